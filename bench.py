@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — SSRS hot path on B200: track-steps/s (+ updraft/potential field time per grid).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the reference's path, all host threads
+
+A "step" is one pass of stages 3+4 (batched track stepping + presence accumulation, plus the presence
+all-reduce when N > 1) over one batch of tracks on fields that are already resident in HBM; the field
+stages (1: updraft stencil, 2: potential solve) are timed once per run and reported under "fields".
+Workload at N=1: BASELINE.json configs[1] (uniform mode, synthetic 6000x5000 DEM at 10 m, 100k tracks).
+For N>1 every rank steps the same number of tracks (weak scaling), fields replicated, RNG keyed by global
+track id, presence maps summed with one NCCL all-reduce inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "track-steps/sec"
+UNIT = "track-steps/s"
+STEP_BYTES = 76          # 72 B of 3x3 gathers on two f32 fields + 4 B presence atomic (no trajectory store)
+STENCIL_BYTES = 20       # 4 B DEM + 4 outputs x 4 B
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ssrs_b200", choices=["ssrs_b200", "reference"])
+    ap.add_argument("--rows", type=int, default=5000)
+    ap.add_argument("--cols", type=int, default=6000)
+    ap.add_argument("--resolution", type=float, default=10.0)
+    ap.add_argument("--tracks-per-gpu", type=int, default=100_000)
+    ap.add_argument("--seed", type=int, default=2021)
+    ap.add_argument("--no-solve", action="store_true", help="skip stage 2 and use a stand-in potential (debug only)")
+    ap.add_argument("--cpu-sample-tracks", type=int, default=0, help="tracks in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a, n):
+    return (f"uniform mode, synthetic {a.cols}x{a.rows} DEM at {a.resolution:g} m, wind 10 m/s from 270 deg, "
+            f"{a.tracks_per_gpu * n} northbound tracks ({a.tracks_per_gpu}/GPU)")
+
+
+def start_cells(a, n_total):
+    """track_start_region=(5,55,1,2) km scaled to the grid, drawn like get_starting_indices('random')."""
+    from ssrs_b200.movmodel import get_starting_indices
+    width_km = (a.cols * a.resolution / 1000.0, a.rows * a.resolution / 1000.0)
+    region = (width_km[0] * 5 / 60, width_km[0] * 55 / 60, width_km[1] * 1 / 50, width_km[1] * 2 / 50)
+    st = np.random.get_state()
+    np.random.seed(a.seed)
+    r, c = get_starting_indices(n_total, region, "random", width_km, a.resolution)
+    np.random.set_state(st)
+    return r, c
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_rate(U, P, shape, sr, sc, n_sample, threads, seed):
+    """C restatement of the reference's stepper (oracle/ssrs_oracle.c) on `threads` host threads."""
+    from oracle import oracle_c as OC
+    st = np.stack([sr[:n_sample], sc[:n_sample]], 1).astype(np.int32)
+    t0 = time.perf_counter()
+    out = OC.step_tracks(U, P, shape, st, 0.0, 1, 1.0, seed=seed, want_presence=True, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return out["total_steps"] / dt, out["total_steps"], dt
+
+
+def build_fields_gpu(a, torch):
+    """Stage 1 (+2) on the device; returns (updraft, potential, info)."""
+    from ssrs_b200 import layers
+    from ssrs_b200.synth import synthetic_dem
+    z = torch.from_numpy(synthetic_dem(a.rows, a.cols, a.resolution)).cuda()
+    info = {}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(3):
+        out = layers.updraft_fields(z, a.resolution, 10.0, 270.0, 0.75)
+    torch.cuda.synchronize()
+    reps = 10
+    ev[0].record()
+    for _ in range(reps):
+        out = layers.updraft_fields(z, a.resolution, 10.0, 270.0, 0.75)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    peak, _ = measured_peak()
+    gbs = STENCIL_BYTES * a.rows * a.cols / (ms * 1e-3) / 1e9
+    info["updraft_ms"] = ms
+    info["updraft_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                "bytes_per_cell": STENCIL_BYTES}
+    up = out["updraft"]
+    pot = None
+    if not a.no_solve:
+        try:
+            from ssrs_b200.potential import solve_potential_device
+        except ImportError:
+            solve_potential_device = None
+        if solve_potential_device is not None:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pot, stats = solve_potential_device(up, 0.0)
+            torch.cuda.synchronize()
+            info["potential_ms"] = (time.perf_counter() - t0) * 1e3
+            info["potential_stats"] = stats
+    if pot is None:
+        yy = torch.linspace(1000.0, 0.0, a.rows, device="cuda")[:, None]
+        pot = (yy + 5.0 * torch.sin(torch.arange(a.cols, device="cuda")[None, :] / 97.0)).float().contiguous()
+        info["potential"] = "stand-in ramp (stage 2 skipped)"
+    return up, pot, info
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    from ssrs_b200 import movmodel as mm
+    from ssrs_b200 import _native as N
+
+    N.load()                     # fail loudly if the CUDA library is missing
+    N.require_cuda()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_per = a.tracks_per_gpu
+    n_total = n_per * world
+    sr_all, sc_all = start_cells(a, n_total)
+    sr, sc = sr_all[rank * n_per:(rank + 1) * n_per], sc_all[rank * n_per:(rank + 1) * n_per]
+    up, pot, finfo = build_fields_gpu(a, torch)
+    fields = mm.interleave_fields(up, pot)
+    presence = torch.zeros((a.rows, a.cols), dtype=torch.int32, device="cuda")
+    total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    shape = (a.rows, a.cols)
+
+    def one_step():
+        presence.zero_()
+        mm.simulate_tracks_batch(0.0, sr, sc, shape, fields=fields, seed=a.seed, track_id0=rank * n_per,
+                                 presence=presence, total_steps=total)
+        if world > 1:
+            dist.all_reduce(presence)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        one_step()
+    barrier()
+    total.zero_()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        presence.zero_()
+        kev[i][0].record()
+        mm.simulate_tracks_batch(0.0, sr, sc, shape, fields=fields, seed=a.seed, track_id0=rank * n_per,
+                                 presence=presence, total_steps=total)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_reduce(presence)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
+    steps_rank = int(total.item())
+    t = torch.tensor([ms_total, float(steps_rank), kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, steps_all, kernel_ms = float(tmax[0]), float(tsum[1]), float(tmax[2])
+    else:
+        steps_all = float(steps_rank)
+    value = steps_all / (ms_total * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (H2D + D2H inside the timed region) ----
+    up_h = torch.empty((a.rows, a.cols), dtype=torch.float32).pin_memory()
+    pot_h = torch.empty((a.rows, a.cols), dtype=torch.float32).pin_memory()
+    up_h.copy_(up)
+    pot_h.copy_(pot)
+    pres_h = torch.empty((a.rows, a.cols), dtype=torch.int32).pin_memory()
+    start_h = np.stack([sr, sc], 1)
+    tot_e2e = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def e2e_step():
+        u_d = up_h.to("cuda", non_blocking=True)
+        p_d = pot_h.to("cuda", non_blocking=True)
+        r = mm.simulate_tracks_batch(0.0, start_h[:, 0], start_h[:, 1], shape, updraft_field=u_d, potential_field=p_d,
+                                     seed=a.seed, track_id0=rank * n_per, total_steps=tot_e2e)
+        if world > 1:
+            dist.all_reduce(r.presence)
+        pres_h.copy_(r.presence, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    tot_e2e.zero_()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(a.steps):
+        e2e_step()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t2 = torch.tensor([ms_e2e, float(tot_e2e.item())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        m = t2.clone(); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        s = t2.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        ms_e2e, steps_e2e = float(m[0]), float(s[1])
+    else:
+        steps_e2e = float(t2[1])
+    e2e_value = steps_e2e / (ms_e2e * 1e-3)
+    h2d = 2 * a.rows * a.cols * 4 + n_per * 8
+    d2h = a.rows * a.cols * 4
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        steps_per_launch = steps_rank / a.steps
+        achieved = STEP_BYTES * steps_per_launch / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (probabilities) on f32 fields", "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "grid": [a.rows, a.cols], "tracks_per_gpu": n_per,
+                       "track_steps_per_step": steps_all / a.steps, "l2": "inputs_exceed_l2 (fields 240 MB > 126 MB)",
+                       "rng": "philox4x32-10 keyed by (seed, global track id, step)",
+                       "parallelism": f"tracks sharded over {world} GPU(s), fields replicated, presence all-reduce"},
+            "fields": finfo,
+            "roofline": {"bound": "hbm", "kernel": "step_tracks_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_track_step": STEP_BYTES, "kernel_ms": kernel_ms,
+                         "note": "gather-latency/L2 bound by design (SURVEY §8d); HBM fraction reported as the contract asks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": a.steps * 1,
+            "clocks": sampler.summary(),
+        }
+        # CPU baseline: the C port of the reference stepper on all host threads, bounded sample
+        threads = os.cpu_count() or 1
+        n_sample = a.cpu_sample_tracks or min(n_per, 256 * threads)
+        U = up.cpu().numpy()
+        P = pot.cpu().numpy()
+        rate, nsteps, dt = cpu_port_rate(U, P, shape, sr, sc, n_sample, threads, a.seed)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n_sample} of the same tracks on the same fields, {nsteps} track-steps in {dt:.1f} s "
+                                          f"(oracle/ssrs_oracle.c, OpenMP); the reference's own Python stepper runs "
+                                          f"~1e4 track-steps/s/core (BASELINE.md)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(a):
+    """CPU arm: the oracle port of the reference's stepper on all host threads, bounded sample per step,
+    same config/metric.  Fields come from the numpy restatement of stage 1; stage 2 (SuperLU) cannot run at
+    this grid size, so the potential is the product's when a GPU is present, else the ramp."""
+    from oracle import oracle_np as O
+    from ssrs_b200.synth import synthetic_dem
+    threads = os.cpu_count() or 1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    z = synthetic_dem(a.rows, a.cols, a.resolution)
+    t0 = time.perf_counter()
+    _, _, _, K = O.updraft_pipeline(z, a.resolution, 10.0, 270.0, 0.75)
+    stencil_s = time.perf_counter() - t0
+    U = K.astype(np.float32)
+    P = None
+    pot_src = "stand-in ramp"
+    try:
+        import torch
+        if torch.cuda.is_available() and not a.no_solve:
+            from ssrs_b200.potential import solve_potential_device
+            pot, _ = solve_potential_device(torch.from_numpy(U).cuda(), 0.0)
+            P = pot.cpu().numpy()
+            pot_src = "ssrs_b200 GPU solve (the reference's SuperLU solve cannot run at this size)"
+    except Exception:
+        P = None
+    if P is None:
+        yy = np.linspace(1000.0, 0.0, a.rows, dtype=np.float32)[:, None]
+        P = (yy + 5.0 * np.sin(np.arange(a.cols, dtype=np.float32)[None, :] / 97.0)).astype(np.float32)
+    n_total = a.tracks_per_gpu * world
+    sr, sc = start_cells(a, n_total)
+    n_sample = a.cpu_sample_tracks or min(n_total, 128 * threads)
+    shape = (a.rows, a.cols)
+    for _ in range(min(a.warmup, 1)):
+        cpu_port_rate(U, P, shape, sr, sc, max(8, n_sample // 8), threads, a.seed)
+    steps_done, secs = 0, 0.0
+    for i in range(a.steps):
+        lo = (i * n_sample) % max(1, n_total - n_sample + 1)
+        rate, nsteps, dt = cpu_port_rate(U, P, shape, sr[lo:], sc[lo:], n_sample, threads, a.seed)
+        steps_done += nsteps
+        secs += dt
+    value = steps_done / secs
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 (probabilities) on f32 fields", "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "grid": [a.rows, a.cols], "potential": pot_src,
+                       "stencil_numpy_s": stencil_s},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n_sample} tracks per step ({steps_done // a.steps} track-steps), "
+                                       f"oracle/ssrs_oracle.c with OpenMP on {threads} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,114 @@
+/* ssrs_b200 — C-ABI of the B200-native SSRS hot path.
+ *
+ * The reference (NREL/SSRS) has no FFI layer: its hot path is the set of Python functions in
+ * ssrs/layers.py and ssrs/movmodel.py that ssrs/simulator.py:21-28 imports.  Each entry point below
+ * replaces one of those functions (cited per function as file:line under /root/reference) and is what
+ * a ctypes binding inside the reference would call (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - rasters are C-contiguous [row][col], row 0 = south, as the reference's flipped rasters
+ *     (ssrs/raster.py:49); gridsize = (rows, cols) = (ysize, xsize) (ssrs/simulator.py:71-73);
+ *   - the caller owns all memory; nothing here allocates persistent device memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on it unless stated otherwise;
+ *   - return value: 0 on success, negative ssrs_status on failure; ssrs_last_error() gives the text.
+ *     Nothing throws across this boundary and there is no CPU fallback: without a CUDA device every
+ *     compute entry point returns SSRS_ERR_CUDA.
+ */
+#ifndef SSRS_B200_H
+#define SSRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSRS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SSRS_API __attribute__((visibility("default")))
+#else
+#define SSRS_API
+#endif
+
+typedef enum ssrs_status {
+    SSRS_OK = 0,
+    SSRS_ERR_INVALID = -1,     /* bad argument (the Python layer raises ValueError) */
+    SSRS_ERR_CUDA = -2,        /* CUDA runtime / driver error, or no device */
+    SSRS_ERR_UNSUPPORTED = -3, /* valid request outside the implemented range */
+    SSRS_ERR_NOT_CONVERGED = -4
+} ssrs_status;
+
+SSRS_API int ssrs_abi_version(void);
+SSRS_API const char* ssrs_last_error(void);
+/* sm_count / compute capability of the current device */
+SSRS_API int ssrs_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 — orographic updraft.  Replaces, fused in one pass over the DEM:
+ *   compute_slope_degrees      ssrs/layers.py:63-93
+ *   compute_aspect_degrees     ssrs/layers.py:96-128
+ *   compute_orographic_updraft ssrs/layers.py:11-22
+ *   get_above_threshold_speed  ssrs/layers.py:171-185   (on the float32-rounded orograph, as
+ *                              ssrs/simulator.py:198,233 round-trips it through a float32 .npy)
+ * wspeed/wdirn: per-cell wind [rows][cols] (snapshot/seasonal modes) or both NULL to use the
+ * uniform scalars (ssrs/simulator.py:194-195).  Any of the four outputs may be NULL.
+ * Border cells of every output are 0 (nan_to_num of the reference's NaN border).
+ */
+SSRS_API int ssrs_updraft(const float* dem, int rows, int cols, float resolution,
+                 const float* wspeed, const float* wdirn,
+                 float uniform_wspeed, float uniform_wdirn_deg,
+                 float threshold,
+                 float* slope_deg, float* aspect_deg, float* orograph, float* updraft,
+                 void* stream);
+
+/* get_above_threshold_speed alone (ssrs/layers.py:171-185) for rasters that did not come from
+ * ssrs_updraft (e.g. orograph + thermals, ssrs/simulator.py:236-242). */
+SSRS_API int ssrs_threshold(const float* in, float* out, int64_t n, float threshold, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3+4 — batched track stepping with fused presence accumulation.  Replaces
+ *   generate_simulated_tracks  ssrs/movmodel.py:264-318  (one call per track in the reference,
+ *                              mapped over a process pool at ssrs/simulator.py:360-369)
+ *   compute_presence_counts    ssrs/movmodel.py:410-419  (fused: every appended point is counted)
+ *
+ * fields: interleaved {updraft, potential} pairs [rows][cols][2] built by ssrs_interleave_fields,
+ *         or NULL for the 'drw' movement model (no fields, ssrs/simulator.py:370-381).
+ * start_rc: int32 [n_tracks][2] (row, col) from get_starting_indices (ssrs/movmodel.py:144-182).
+ * dirprob9_host: HOST pointer to the 9 weights of get_directional_probs(move_dirn*pi/180)
+ *         (ssrs/movmodel.py:247-257), computed by the caller exactly as the reference does.
+ * memory, nu: track_dirn_restrict and track_stochastic_nu (ssrs/config.py:56-57).
+ * Random numbers: if uniforms != NULL ("verification mode") step k of track t consumes
+ *         uniforms[t*uniforms_stride + k] — the reference's pre-drawn np.random stream; otherwise
+ *         Philox4x32-10 keyed by seed with counter (track_id0 + t, k), so results do not depend on
+ *         how tracks are sharded over GPUs.
+ * traj (optional): int16 [traj_cap][n_tracks][2] step-major (row, col); points beyond traj_cap are
+ *         not stored but still stepped and counted.   traj_len (optional): int32 [n_tracks] number of
+ *         trajectory points (= steps + 1).   presence (optional): uint32 [rows][cols], incremented
+ *         atomically (not cleared).   total_steps (optional): one uint64, incremented by the number
+ *         of track-steps taken (loop iterations at ssrs/movmodel.py:285-317).
+ */
+SSRS_API int ssrs_step_tracks(const float* fields, int rows, int cols,
+                     const int32_t* start_rc, int64_t n_tracks, int64_t track_id0,
+                     const double* dirprob9_host, int memory, double nu,
+                     uint64_t seed, const double* uniforms, int64_t uniforms_stride,
+                     int16_t* traj, int64_t traj_cap, int32_t* traj_len,
+                     uint32_t* presence, unsigned long long* total_steps,
+                     void* stream);
+
+/* {updraft, potential} -> interleaved pairs (one 8-byte gather per cell in the stepping kernel). */
+SSRS_API int ssrs_interleave_fields(const float* updraft, const float* potential, float* fields,
+                           int64_t n, void* stream);
+
+/* compute_presence_counts (ssrs/movmodel.py:410-419) for stored trajectories:
+ * traj int16 [traj_cap][n_tracks][2] step-major + traj_len as written by ssrs_step_tracks. */
+SSRS_API int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len,
+                         int64_t n_tracks, int rows, int cols, uint32_t* presence, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSRS_B200_H */

@@ -1,0 +1,171 @@
+/* TEST INFRASTRUCTURE ONLY — plain-C restatement of the SSRS track stepper and presence count.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load the library built
+ * from this file; the product (ssrs_b200/) never does.  It restates, line for line,
+ *   generate_simulated_tracks      /root/reference/ssrs/movmodel.py:264-318
+ *   move_away_from_boundary        /root/reference/ssrs/movmodel.py:205-217
+ *   get_track_restrictions         /root/reference/ssrs/movmodel.py:185-202  (as a table)
+ *   generate_move_probabilities    /root/reference/ssrs/movmodel.py:220-244
+ *   np.random.choice(range(9), p)  numpy legacy: cdf = cumsum(p); cdf /= cdf[-1];
+ *                                  searchsorted(u, 'right') with ONE random_sample() per call
+ *   compute_presence_counts        /root/reference/ssrs/movmodel.py:410-419  (int32, no int16 wrap)
+ * in the reference's arithmetic: float32 potential differences (:301-304), float64 elsewhere, numpy's
+ * pairwise summation order for the 9-element sums.  Pinned by tests/test_oracle_golden.py against
+ * trajectories produced by the unmodified reference (tests/golden/, made by oracle/make_golden.py).
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC  (oracle/build_oracle.py).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static const unsigned RESTRICT_LUT[9] = {0x00B, 0x007, 0x026, 0x049, 0x1EF, 0x124, 0x0C8, 0x1C0, 0x1A0};
+
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t* o0, uint32_t* o1) {
+    for (int i = 0; i < 10; ++i) {
+        uint64_t m0 = (uint64_t)0xD2511F53u * c0, m1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(m1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)m1;
+        uint32_t n2 = (uint32_t)(m0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)m0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    *o0 = c0; *o1 = c1;
+}
+
+double oracle_philox_uniform(uint64_t seed, uint64_t track, uint32_t step) {
+    uint32_t a, b;
+    philox4x32_10((uint32_t)track, (uint32_t)(track >> 32), step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), &a, &b);
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+static double pairwise9(const double* p) {
+    return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
+}
+
+/* One track.  U (float32, widened to double as the reference's float64 updraft) and P (float32) are
+ * [rows][cols]; either both given (fluid-flow) or both NULL ('drw').  uniforms: per-step numbers for this
+ * track or NULL for Philox(seed, gid, k).  traj: optional int16 [cap][2].  presence: optional int32
+ * [rows][cols] (incremented; atomically when built with OpenMP).  Returns the number of points. */
+static int64_t one_track(const float* U, const float* P, int nr, int nc, int row, int col, const double* dirp,
+                         int memory, double nu, uint64_t seed, uint64_t gid, const double* uniforms,
+                         int16_t* traj, int64_t cap, int32_t* presence) {
+    const int burnin = (int)((nr < nc ? nr : nc) / 10);                /* :276 */
+    const double max_moves = (double)nr / 2 * (double)nc / 2;          /* :277 */
+    const float ninv_d = 0.70710677f;
+    int hist_len = 1, hist_cap = 64;
+    unsigned char* hist = (unsigned char*)malloc((size_t)hist_cap);    /* directions list, :280-281 */
+    hist[0] = 4;
+    int64_t k = 0;
+    if (traj && cap > 0) { traj[0] = (int16_t)row; traj[1] = (int16_t)col; }
+    if (presence) {
+#pragma omp atomic
+        presence[(int64_t)row * nc + col] += 1;
+    }
+    while ((double)k < max_moves) {                                    /* :285 */
+        int r = row, c = col;
+        if (k > burnin) {                                              /* :287-289 */
+            if (!(0 < r && r < nr - 1 && 0 < c && c < nc - 1)) break;
+        } else {                                                       /* :290-291 */
+            if (r <= 1) r += 2; else if (r >= nr - 2) r -= 2;
+            if (c <= 0) c += 2; else if (c >= nc - 2) c -= 2;
+        }
+        unsigned mask = 0x1EF;                                         /* :307-309 */
+        {
+            int m = (memory == 0 || memory > hist_len) ? hist_len : memory;   /* directions[-0:] is the whole list */
+            for (int j = 0; j < m; ++j) mask &= RESTRICT_LUT[hist[hist_len - 1 - j]];
+        }
+        double p[9];
+        int any_nan = 0;
+        if (U != NULL) {
+            const int64_t o = (int64_t)r * nc + c;
+            double uc = (double)U[o]; if (uc < 1e-06) uc = 1e-06;      /* :295 */
+            const double iuc = 1.0 / uc;
+            for (int i = 0; i < 9; ++i) {
+                const int dr = i / 3 - 1, dc = i % 3 - 1;
+                const int64_t q = o + (int64_t)dr * nc + dc;
+                double ui = (double)U[q]; if (ui < 1e-06) ui = 1e-06;
+                const double w = 2.0 / (iuc + 1.0 / ui);               /* :296, :260-261 */
+                const float ninv = (i == 4) ? 0.0f : ((dr != 0 && dc != 0) ? ninv_d : 1.0f);
+                const float d = (float)(P[o] - P[q]) * ninv;           /* float32, :301-304 */
+                p[i] = w * (double)d;                                  /* :305 */
+                if (p[i] != p[i]) any_nan = 1;
+            }
+        } else {
+            for (int i = 0; i < 9; ++i) p[i] = dirp[i];                /* :298-299 */
+        }
+        if (any_nan) for (int i = 0; i < 9; ++i) p[i] = dirp[i];       /* :228-230 */
+        int nz = 0;
+        for (int i = 0; i < 9; ++i) {                                  /* :231-233 */
+            if (p[i] < 0.0) p[i] = 0.0;
+            if (i == 4 || !((mask >> i) & 1u)) p[i] = 0.0;
+            if (p[i] != 0.0) nz++;
+        }
+        if (nz == 0) {                                                 /* :234-238 */
+            for (int i = 0; i < 9; ++i) {
+                p[i] = (i == 4 || !((mask >> i) & 1u)) ? 0.0 : dirp[i];
+                if (p[i] != 0.0) nz++;
+            }
+        }
+        if (nz == 0) for (int i = 0; i < 9; ++i) p[i] = dirp[i];       /* :239-240 */
+        double s = pairwise9(p);                                       /* :241 */
+        for (int i = 0; i < 9; ++i) p[i] = p[i] / s;
+        if (nu != 1.0) for (int i = 0; i < 9; ++i) p[i] = pow(p[i], nu);   /* :242 */
+        s = pairwise9(p);                                              /* :243 */
+        for (int i = 0; i < 9; ++i) p[i] = p[i] / s;
+        const double u = uniforms ? uniforms[k] : oracle_philox_uniform(seed, gid, (uint32_t)k);
+        double cdf[9];
+        cdf[0] = p[0];
+        for (int i = 1; i < 9; ++i) cdf[i] = cdf[i - 1] + p[i];
+        const double tot = cdf[8];
+        int idx = 0;
+        for (int i = 0; i < 9; ++i) if (cdf[i] / tot <= u) idx++;      /* searchsorted side='right' */
+        if (idx > 8) idx = 8;
+        row = r + (idx / 3 - 1);                                       /* :313-317 */
+        col = c + (idx % 3 - 1);
+        ++k;
+        if (hist_len == hist_cap) { hist_cap *= 2; hist = (unsigned char*)realloc(hist, (size_t)hist_cap); }
+        hist[hist_len++] = (unsigned char)idx;
+        if (traj && k < cap) { traj[2 * k] = (int16_t)row; traj[2 * k + 1] = (int16_t)col; }
+        if (presence) {
+#pragma omp atomic
+            presence[(int64_t)row * nc + col] += 1;
+        }
+    }
+    free(hist);
+    return k + 1;
+}
+
+/* Batch driver.  start_rc int32 [n][2]; uniforms [n][ustride] or NULL; traj int16 [n][cap][2] track-major
+ * or NULL; traj_len int32 [n] or NULL; presence int32 [rows][cols] or NULL.  Returns total track-steps. */
+int64_t oracle_step_tracks(const float* U, const float* P, int rows, int cols, const int32_t* start_rc, int64_t n,
+                           int64_t track_id0, const double* dirp, int memory, double nu, uint64_t seed,
+                           const double* uniforms, int64_t ustride, int16_t* traj, int64_t cap, int32_t* traj_len,
+                           int32_t* presence, int nthreads) {
+    int64_t total = 0;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : total) num_threads(nthreads)
+#endif
+    for (int64_t t = 0; t < n; ++t) {
+        int64_t len = one_track(U, P, rows, cols, start_rc[2 * t], start_rc[2 * t + 1], dirp, memory, nu, seed,
+                                (uint64_t)(track_id0 + t), uniforms ? uniforms + t * ustride : NULL,
+                                traj ? traj + t * cap * 2 : NULL, cap, presence);
+        if (traj_len) traj_len[t] = (int32_t)len;
+        total += len - 1;
+    }
+    return total;
+}
+
+/* compute_presence_counts, movmodel.py:410-419, for track-major trajectories. */
+void oracle_presence_counts(const int16_t* traj, int64_t cap, const int32_t* traj_len, int64_t n, int rows, int cols,
+                            int32_t* presence) {
+    for (int64_t t = 0; t < n; ++t) {
+        int64_t len = traj_len[t] < cap ? traj_len[t] : cap;
+        for (int64_t k = 0; k < len; ++k) {
+            int r = traj[(t * cap + k) * 2], c = traj[(t * cap + k) * 2 + 1];
+            if (r >= 0 && r < rows && c >= 0 && c < cols) presence[(int64_t)r * cols + c] += 1;
+        }
+    }
+}

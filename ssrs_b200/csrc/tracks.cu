@@ -1,0 +1,312 @@
+// Stage 3+4 — batched stochastic track stepping with fused presence accumulation (sm_100a).
+//
+// Replaces generate_simulated_tracks (ssrs/movmodel.py:264-318, one Python call per track mapped over a
+// fork pool at ssrs/simulator.py:360-369) and compute_presence_counts (ssrs/movmodel.py:410-419).
+//
+// One thread owns one track at a time and steps it to completion; when its track ends the lane
+// immediately takes the next unstarted track (lane-level refill), so warps stay full although track
+// lengths differ.  Per step a lane gathers the centre cell and the neighbours its direction-memory mask
+// allows from the interleaved {updraft, potential} raster (one 8-byte read-only load each), evaluates the
+// move probabilities in the reference's exact arithmetic (float32 potential differences, float64
+// everything else, numpy's pairwise-sum order), draws one uniform (caller-supplied in verification mode,
+// else counter-based Philox4x32-10 keyed by (seed, global track id, step)), and appends the new point:
+// a coalesced step-major int16x2 store and one `red.global.add.u32` on the presence raster.
+//
+// This translation unit is compiled with -fmad=false: float64 products and sums must round separately
+// to reproduce numpy bit for bit.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace ssrs {
+namespace {
+
+// direction-memory masks, get_track_restrictions (movmodel.py:185-202) as a table; bit i = flat move
+// index 3*(dr+1)+(dc+1).  Previous move SW,S,SE,W,(0,0),E,NW,N,NE:
+//   0x00B 0x007 0x026 0x049 0x1EF 0x124 0x0C8 0x1C0 0x1A0     packed 9 bits each into two words.
+constexpr unsigned long long LUT_A = (0x00BULL) | (0x007ULL << 9) | (0x026ULL << 18) | (0x049ULL << 27) |
+                                     (0x1EFULL << 36) | (0x124ULL << 45) | (0x0C8ULL << 54);
+constexpr unsigned long long LUT_B = (0x1C0ULL) | (0x1A0ULL << 9);
+
+__device__ __forceinline__ unsigned restrict_mask(unsigned move) {
+    unsigned long long w = move < 7 ? (LUT_A >> (9 * move)) : (LUT_B >> (9 * (move - 7)));
+    return (unsigned)w & 0x1FFu;
+}
+
+struct TrackParams {
+    const float2* fields;
+    const int2* start;
+    const double* uniforms;
+    short2* traj;
+    int* traj_len;
+    unsigned* presence;
+    unsigned long long* total_steps;
+    long long n_tracks, track_id0, ustride, traj_cap;
+    unsigned long long seed;
+    double dirp[9];
+    double nu;
+    double max_moves;
+    int rows, cols, burnin, memory, nu_is_one;
+};
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (track_lo, track_hi, step_lo, step_hi), key = seed.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                              unsigned k1, unsigned& o0, unsigned& o1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+
+__device__ __forceinline__ double uniform53(unsigned a, unsigned b) {
+    // numpy's random_sample recipe: 27 + 26 random bits -> [0,1)
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double pairwise9(const double* p) {
+    // numpy add.reduce over 9 contiguous float64: 8 accumulators folded pairwise, then the tail
+    return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
+}
+
+template <bool HAS_FIELDS>
+__global__ void __launch_bounds__(128, 4) step_tracks_kernel(const TrackParams P) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nr = P.rows, nc = P.cols;
+    const float NINV_D = 0.70710677f;     // float32(1/sqrt(2)), movmodel.py:139-141
+    unsigned long long steps_local = 0;
+    bool alive = false;
+    int row = 0, col = 0, k = 0;
+    unsigned long long hist = 4;          // 4-bit move codes, most recent in the low nibble
+    int hcount = 1;
+    unsigned run_mask = 0x1EF;            // AND over the whole history (memory == 0)
+
+    while (true) {
+        if (!alive) {
+            if (t >= P.n_tracks) break;
+            int2 s = __ldg(P.start + t);
+            row = s.x; col = s.y; k = 0; hist = 4; hcount = 1; run_mask = 0x1EF;
+            if (P.traj != nullptr && P.traj_cap > 0) P.traj[t] = make_short2((short)row, (short)col);
+            if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
+            alive = true;
+        }
+        int r = row, c = col;
+        bool finish = !((double)k < P.max_moves);                           // movmodel.py:285
+        if (!finish) {
+            if (k > P.burnin) {                                             // :287-289
+                finish = !(0 < r && r < nr - 1 && 0 < c && c < nc - 1);
+            } else {                                                        // :290-291, :205-217
+                if (r <= 1) r += 2; else if (r >= nr - 2) r -= 2;
+                if (c <= 0) c += 2; else if (c >= nc - 2) c -= 2;
+            }
+        }
+        if (finish) {
+            if (P.traj_len != nullptr) P.traj_len[t] = k + 1;
+            steps_local += (unsigned long long)k;
+            alive = false;
+            t += stride;
+            continue;
+        }
+        // direction-memory mask (:307-309)
+        unsigned mask;
+        if (P.memory == 1) mask = restrict_mask((unsigned)(hist & 15));
+        else if (P.memory == 0) mask = run_mask;
+        else {
+            mask = 0x1EF;
+            int m = P.memory < hcount ? P.memory : hcount;
+            for (int j = 0; j < m; ++j) mask &= restrict_mask((unsigned)((hist >> (4 * j)) & 15));
+        }
+        double p[9];
+        bool any_nz = false, any_nan = false;
+        if (HAS_FIELDS) {
+            const float2* base = P.fields + (long long)r * nc + c;
+            const float2 fc = __ldg(base);
+            const double uc = fmax((double)fc.x, 1e-06);                    // :295
+            const double iuc = 1.0 / uc;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                p[i] = 0.0;
+                if (i != 4 && ((mask >> i) & 1u)) {
+                    const int dr = i / 3 - 1, dc = i % 3 - 1;
+                    const float2 f = __ldg(base + dr * nc + dc);
+                    const double ui = fmax((double)f.x, 1e-06);
+                    const double w = 2.0 / (iuc + 1.0 / ui);                // :296, :260-261
+                    const float ninv = (dr != 0 && dc != 0) ? NINV_D : 1.0f;
+                    const float d = __fmul_rn(__fsub_rn(fc.y, f.y), ninv);  // float32, :301-304
+                    double v = w * (double)d;                               // :305
+                    any_nan |= (v != v);
+                    v = v > 0.0 ? v : 0.0;                                  // clip(min=0), :231
+                    p[i] = v;
+                    any_nz |= (v != 0.0);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {                                    // 'drw': p = directional, :298-299
+                p[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0;
+                any_nz |= (p[i] != 0.0);
+            }
+        }
+        if (any_nan || !any_nz) {                                           // :228-230, :234-236
+            any_nz = false;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                p[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0;
+                any_nz |= (p[i] != 0.0);
+            }
+            if (!any_nz) {                                                  // :239-240 (mask ignored)
+#pragma unroll
+                for (int i = 0; i < 9; ++i) p[i] = P.dirp[i];
+            }
+        }
+        double s = pairwise9(p);                                            // :241
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p[i] = (p[i] != 0.0) ? p[i] / s : 0.0;
+        if (!P.nu_is_one) {                                                 // :242
+#pragma unroll
+            for (int i = 0; i < 9; ++i) p[i] = pow(p[i], P.nu);
+        }
+        s = pairwise9(p);                                                   // :243
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p[i] = (p[i] != 0.0) ? p[i] / s : 0.0;
+        // np.random.choice (:312): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, side='right')
+        double u;
+        if (P.uniforms != nullptr) {
+            u = __ldg(P.uniforms + t * P.ustride + k);
+        } else {
+            const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
+            unsigned a, b;
+            philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)k, 0u, (unsigned)P.seed,
+                          (unsigned)(P.seed >> 32), a, b);
+            u = uniform53(a, b);
+        }
+        double cdf[9];
+        cdf[0] = p[0];
+#pragma unroll
+        for (int i = 1; i < 9; ++i) cdf[i] = cdf[i - 1] + p[i];
+        const double tot = cdf[8];
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) idx += ((cdf[i] / tot) <= u) ? 1 : 0;
+        idx = idx > 8 ? 8 : idx;
+        row = r + (idx / 3 - 1);                                            // :313-317
+        col = c + (idx % 3 - 1);
+        ++k;
+        hist = (hist << 4) | (unsigned long long)idx;
+        hcount = hcount < 16 ? hcount + 1 : 16;
+        run_mask &= restrict_mask((unsigned)idx);
+        if (P.traj != nullptr && (long long)k < P.traj_cap)
+            P.traj[(long long)k * P.n_tracks + t] = make_short2((short)row, (short)col);
+        if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
+    }
+    if (P.total_steps != nullptr) {
+        // one atomic per warp
+        for (int o = 16; o > 0; o >>= 1) steps_local += __shfl_down_sync(0xffffffffu, steps_local, o);
+        if ((threadIdx.x & 31) == 0 && steps_local) atomicAdd(P.total_steps, steps_local);
+    }
+}
+
+__global__ void interleave_kernel(const float* __restrict__ u, const float* __restrict__ p, float2* __restrict__ out,
+                                  long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = make_float2(__ldcs(u + i), __ldcs(p + i));
+}
+
+__global__ void presence_from_traj_kernel(const short2* __restrict__ traj, long long traj_cap,
+                                          const int* __restrict__ len, long long n_tracks, int rows, int cols,
+                                          unsigned* presence) {
+    const long long total = traj_cap * n_tracks;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long k = i / n_tracks, t = i - k * n_tracks;
+        if (k < (long long)__ldg(len + t)) {
+            const short2 pt = traj[i];
+            if (pt.x >= 0 && pt.x < rows && pt.y >= 0 && pt.y < cols)
+                atomicAdd(presence + (long long)pt.x * cols + pt.y, 1u);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace ssrs
+
+using namespace ssrs;
+
+extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const int32_t* start_rc, int64_t n_tracks,
+                                int64_t track_id0, const double* dirprob9_host, int memory, double nu, uint64_t seed,
+                                const double* uniforms, int64_t uniforms_stride, int16_t* traj, int64_t traj_cap,
+                                int32_t* traj_len, uint32_t* presence, unsigned long long* total_steps,
+                                void* stream) {
+    SSRS_REQUIRE(rows >= 5 && cols >= 5, "ssrs_step_tracks: grid %dx%d too small", rows, cols);
+    SSRS_REQUIRE(rows <= 32767 && cols <= 32767, "ssrs_step_tracks: int16 trajectories need rows, cols <= 32767");
+    SSRS_REQUIRE(n_tracks >= 0 && track_id0 >= 0, "ssrs_step_tracks: negative track count or id");
+    SSRS_REQUIRE(start_rc != nullptr || n_tracks == 0, "ssrs_step_tracks: start_rc is NULL");
+    SSRS_REQUIRE(dirprob9_host != nullptr, "ssrs_step_tracks: dirprob9_host is NULL");
+    SSRS_REQUIRE(uniforms == nullptr || uniforms_stride > 0, "ssrs_step_tracks: uniforms_stride must be positive");
+    SSRS_REQUIRE(traj == nullptr || traj_cap > 0, "ssrs_step_tracks: traj given with traj_cap <= 0");
+    if (memory < 0 || memory > 16) {
+        set_error("ssrs_step_tracks: track_dirn_restrict=%d outside the supported range 0..16", memory);
+        return SSRS_ERR_UNSUPPORTED;
+    }
+    if (n_tracks == 0) return SSRS_OK;
+    TrackParams P;
+    P.fields = reinterpret_cast<const float2*>(fields);
+    P.start = reinterpret_cast<const int2*>(start_rc);
+    P.uniforms = uniforms;
+    P.traj = reinterpret_cast<short2*>(traj);
+    P.traj_len = traj_len;
+    P.presence = presence;
+    P.total_steps = total_steps;
+    P.n_tracks = n_tracks; P.track_id0 = track_id0; P.ustride = uniforms_stride; P.traj_cap = traj ? traj_cap : 0;
+    P.seed = seed;
+    for (int i = 0; i < 9; ++i) P.dirp[i] = dirprob9_host[i];
+    P.nu = nu; P.nu_is_one = (nu == 1.0);
+    P.max_moves = (double)rows / 2 * (double)cols / 2;                       // movmodel.py:277
+    P.rows = rows; P.cols = cols;
+    P.burnin = (int)((rows < cols ? rows : cols) / 10);                      // movmodel.py:276
+    P.memory = memory;
+    const int threads = 128;
+    long long blocks = cdiv(n_tracks, threads);
+    const long long cap = (long long)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (fields != nullptr) step_tracks_kernel<true><<<(int)blocks, threads, 0, st>>>(P);
+    else step_tracks_kernel<false><<<(int)blocks, threads, 0, st>>>(P);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int ssrs_interleave_fields(const float* updraft, const float* potential, float* fields, int64_t n,
+                                      void* stream) {
+    SSRS_REQUIRE(updraft && potential && fields, "ssrs_interleave_fields: NULL raster");
+    SSRS_REQUIRE(n >= 0, "ssrs_interleave_fields: negative size");
+    if (n == 0) return SSRS_OK;
+    long long blocks = cdiv(n, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    interleave_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        updraft, potential, reinterpret_cast<float2*>(fields), n);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len, int64_t n_tracks,
+                                    int rows, int cols, uint32_t* presence, void* stream) {
+    SSRS_REQUIRE(traj && traj_len && presence, "ssrs_presence_counts: NULL buffer");
+    SSRS_REQUIRE(traj_cap > 0 && n_tracks >= 0 && rows > 0 && cols > 0, "ssrs_presence_counts: bad sizes");
+    if (n_tracks == 0) return SSRS_OK;
+    long long blocks = cdiv(traj_cap * n_tracks, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    presence_from_traj_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const short2*>(traj), traj_cap, traj_len, n_tracks, rows, cols, presence);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}

@@ -1,0 +1,349 @@
+// Stage 1 — fused slope / aspect / orographic updraft / threshold stencil (sm_100a).
+//
+// Replaces ssrs/layers.py:63-93 (compute_slope_degrees), :96-128 (compute_aspect_degrees),
+// :11-22 (compute_orographic_updraft) and :171-185 (get_above_threshold_speed) with one pass over
+// the DEM.  HBM-bound: 4 B read + 4 B per requested output plane per cell (20 B/cell with all four).
+//
+// Layout: a CTA owns a 32x128 output tile; the (32+2)x(128+8) halo tile of the DEM is staged in
+// shared memory either by TMA (cp.async.bulk.tensor.2d, double-buffered behind mbarriers, persistent
+// CTAs, out-of-bounds rows/cols zero-filled by the hardware) or, when the raster does not meet TMA's
+// 16-byte pitch/alignment rules, by plain coalesced loads.  Each thread computes a 4-row x 4-col patch:
+// one aligned float4 shared-memory read per row, halo columns exchanged with warp shuffles, three rows
+// kept rolling in registers; outputs leave as float4 stores (512 B contiguous per warp and row).
+//
+// Numerics: Horn sums are formed differences-first, which is exact in fp32 for
+// float32 DEMs, so `dz_dx == 0` fires on the same cells as the float64 reference; the updraft itself is
+// evaluated without inverse trig:  sin(atan h) = h / sqrt(1+h^2),
+// cos(aspect - wdir) = -(gy cos(wdir) + gx' sin(wdir)) / hypot(gx', gy)   with gx' = (gx==0 ? 1e-10 : gx).
+#include "common.cuh"
+
+#include <cuda.h>
+#include <math.h>
+
+namespace ssrs {
+namespace {
+
+constexpr int TH = 32;            // tile rows
+constexpr int TW = 128;           // tile cols
+constexpr int HALO_L = 4;         // left halo kept 4 wide so each thread's float4 stays 16B-aligned
+constexpr int SW = TW + 2 * HALO_L;   // 136 floats per staged row
+constexpr int SH = TH + 2;            // 34 staged rows
+constexpr int NTHREADS = 256;
+constexpr int STAGES = 2;
+constexpr uint32_t TILE_BYTES = SW * SH * sizeof(float);
+
+struct UpdraftParams {
+    const float* dem;
+    const float* wspeed;   // per-cell or null
+    const float* wdirn;    // per-cell (degrees) or null
+    float* slope;
+    float* aspect;
+    float* orograph;
+    float* updraft;
+    int rows, cols;
+    int tiles_r, tiles_c;
+    float inv8res;
+    float uni_speed, uni_sin, uni_cos;   // uniform wind: speed, sin/cos of direction
+    float thr, thr_inv, inv_em1;
+    int vec_ok;            // cols % 4 == 0 and all pointers 16B aligned -> float4 global accesses
+};
+
+__device__ __forceinline__ float threshold_fn(float w, float thr, float thr_inv, float inv_em1) {
+    // layers.py:171-180: 0 if w <= 0.01 ; w if w > thr ; thr*(exp((w/thr)^5)-1)/(e-1) otherwise
+    if (!(w > 0.01f)) return 0.0f;
+    if (w > thr) return w;
+    float t = w * thr_inv;
+    float t2 = t * t;
+    return thr * expm1f(t2 * t2 * t) * inv_em1;
+}
+
+// One cell.  Arguments are the nine DEM samples named as in layers.py:80-88 would index them:
+// n* = row r+1, m* = row r, s* = row r-1 ; *w = col c-1, *c = col c, *e = col c+1.
+__device__ __forceinline__ void cell(float sw_, float sc_, float se_, float mw_, float me_,
+                                     float nw_, float nc_, float ne_,
+                                     float inv8res, float V, float sinw, float cosw,
+                                     float& slope, float& aspect, float& oro) {
+    // dz_dx: derivative along axis 0 (rows) ; dz_dy: along axis 1 (cols)   (layers.py:89-90)
+    float gx = ((ne_ - se_) + 2.0f * (nc_ - sc_) + (nw_ - sw_)) * inv8res;
+    float gy = ((se_ - sw_) + 2.0f * (me_ - mw_) + (ne_ - nw_)) * inv8res;
+    float h2 = gx * gx + gy * gy;
+    float h = sqrtf(h2);
+    slope = atanf(h) * 57.29577951308232f;
+    float gxa = (gx == 0.0f) ? 1e-10f : gx;                               // layers.py:124
+    float ang = atanf(gy / gxa) * 57.29577951308232f;
+    aspect = 180.0f - ang + copysignf(90.0f, gxa);                       // layers.py:125-127
+    float ha = sqrtf(gxa * gxa + gy * gy);
+    float cosd = -(gy * cosw + gxa * sinw) / ha;
+    float sins = h * rsqrtf(1.0f + h2);
+    oro = fmaxf(0.0f, V * sins * fmaxf(0.0f, cosd));                      // layers.py:19-22
+}
+
+struct Row6 { float l; float4 v; float r; };
+
+__device__ __forceinline__ Row6 load_row(const float* srow, int lane) {
+    Row6 o;
+    o.v = *reinterpret_cast<const float4*>(srow + HALO_L + 4 * lane);
+    float lft = __shfl_up_sync(0xffffffffu, o.v.w, 1);
+    float rgt = __shfl_down_sync(0xffffffffu, o.v.x, 1);
+    o.l = (lane == 0) ? srow[HALO_L - 1] : lft;
+    o.r = (lane == 31) ? srow[HALO_L + TW] : rgt;
+    return o;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void store4(float* plane, int64_t idx, int c0, int cols, float a, float b, float c, float d) {
+    if (plane == nullptr) return;
+    if (VEC) {
+        if (c0 + 3 < cols) {
+            __stcs(reinterpret_cast<float4*>(plane + idx), make_float4(a, b, c, d));
+            return;
+        }
+    }
+    if (c0 < cols) plane[idx] = a;
+    if (c0 + 1 < cols) plane[idx + 1] = b;
+    if (c0 + 2 < cols) plane[idx + 2] = c;
+    if (c0 + 3 < cols) plane[idx + 3] = d;
+}
+
+// Computes one staged tile.  `tile` points at SH x SW floats; tile origin (r0, c0) in the raster.
+template <bool VEC>
+__device__ __forceinline__ void compute_tile(const UpdraftParams& p, const float* tile, int r0, int c0t) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c0 = c0t + 4 * lane;
+    const int rbase = r0 + 4 * warp;
+    if (rbase >= p.rows) return;                      // warp-uniform
+    const float* s = tile + (4 * warp) * SW;          // staged row index = (row - r0) + 1
+    Row6 below = load_row(s, lane);
+    Row6 mid = load_row(s + SW, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        Row6 above = load_row(s + (i + 2) * SW, lane);
+        const int r = rbase + i;
+        if (r < p.rows) {                             // warp-uniform
+            float sl[4], as[4], oro[4], up[4];
+            const float S[6] = {below.l, below.v.x, below.v.y, below.v.z, below.v.w, below.r};
+            const float M[6] = {mid.l, mid.v.x, mid.v.y, mid.v.z, mid.v.w, mid.r};
+            const float N[6] = {above.l, above.v.x, above.v.y, above.v.z, above.v.w, above.r};
+            const int64_t idx = (int64_t)r * p.cols + c0;
+            float V[4] = {p.uni_speed, p.uni_speed, p.uni_speed, p.uni_speed};
+            float sn[4] = {p.uni_sin, p.uni_sin, p.uni_sin, p.uni_sin};
+            float cs[4] = {p.uni_cos, p.uni_cos, p.uni_cos, p.uni_cos};
+            if (p.wspeed != nullptr) {
+                float wd[4];
+                if (VEC && c0 + 3 < p.cols) {
+                    float4 a = __ldcs(reinterpret_cast<const float4*>(p.wspeed + idx));
+                    float4 b = __ldcs(reinterpret_cast<const float4*>(p.wdirn + idx));
+                    V[0] = a.x; V[1] = a.y; V[2] = a.z; V[3] = a.w;
+                    wd[0] = b.x; wd[1] = b.y; wd[2] = b.z; wd[3] = b.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        bool ok = c0 + j < p.cols;
+                        V[j] = ok ? p.wspeed[idx + j] : 0.0f;
+                        wd[j] = ok ? p.wdirn[idx + j] : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sincospif(wd[j] * (1.0f / 180.0f), &sn[j], &cs[j]);
+            }
+            const bool edge_row = (r == 0) || (r == p.rows - 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                cell(S[j], S[j + 1], S[j + 2], M[j], M[j + 2], N[j], N[j + 1], N[j + 2],
+                     p.inv8res, V[j], sn[j], cs[j], sl[j], as[j], oro[j]);
+                if (edge_row || c == 0 || c >= p.cols - 1) { sl[j] = 0.0f; as[j] = 0.0f; oro[j] = 0.0f; }
+                up[j] = threshold_fn(oro[j], p.thr, p.thr_inv, p.inv_em1);
+            }
+            store4<VEC>(p.slope, idx, c0, p.cols, sl[0], sl[1], sl[2], sl[3]);
+            store4<VEC>(p.aspect, idx, c0, p.cols, as[0], as[1], as[2], as[3]);
+            store4<VEC>(p.orograph, idx, c0, p.cols, oro[0], oro[1], oro[2], oro[3]);
+            store4<VEC>(p.updraft, idx, c0, p.cols, up[0], up[1], up[2], up[3]);
+        }
+        below = mid;
+        mid = above;
+    }
+}
+
+// ---- plain staging: one tile per CTA --------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(NTHREADS) updraft_plain_kernel(const UpdraftParams p) {
+    __shared__ __align__(16) float tile[SH * SW];
+    const int tr = blockIdx.x / p.tiles_c;
+    const int tc = blockIdx.x - tr * p.tiles_c;
+    const int r0 = tr * TH, c0 = tc * TW;
+    for (int i = threadIdx.x; i < SH * SW; i += NTHREADS) {
+        int sr = i / SW, sc = i - sr * SW;
+        int r = r0 - 1 + sr, c = c0 - HALO_L + sc;
+        float v = 0.0f;
+        if (r >= 0 && r < p.rows && c >= 0 && c < p.cols) v = __ldg(p.dem + (int64_t)r * p.cols + c);
+        tile[i] = v;
+    }
+    __syncthreads();
+    compute_tile<VEC>(p, tile, r0, c0);
+}
+
+// ---- TMA staging: persistent CTAs, two-stage mbarrier pipeline ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(NTHREADS) updraft_tma_kernel(const UpdraftParams p,
+                                                               const __grid_constant__ CUtensorMap dem_map) {
+    __shared__ __align__(128) float tiles[STAGES][SH * SW];
+    __shared__ __align__(8) uint64_t full[STAGES];
+    const int ntiles = p.tiles_r * p.tiles_c;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t, int stage) {
+        const int tr = t / p.tiles_c, tc = t - tr * p.tiles_c;
+        mbar_expect_tx(&full[stage], TILE_BYTES);
+        tma_load_2d(tiles[stage], &dem_map, &full[stage], tc * TW - HALO_L, tr * TH - 1);
+    };
+    int t = blockIdx.x;
+    if (threadIdx.x == 0 && t < ntiles) issue(t, 0);
+    uint32_t phase[STAGES] = {0, 0};
+    int stage = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int tnext = t + gridDim.x;
+        if (threadIdx.x == 0 && tnext < ntiles) issue(tnext, stage ^ 1);   // buffer freed by the sync below
+        mbar_wait(&full[stage], phase[stage]);
+        phase[stage] ^= 1;
+        const int tr = t / p.tiles_c, tc = t - tr * p.tiles_c;
+        compute_tile<VEC>(p, tiles[stage], tr * TH, tc * TW);
+        __syncthreads();     // everyone done reading tiles[stage] before it is refilled next-next round
+        stage ^= 1;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+__global__ void threshold_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, float thr,
+                                 float thr_inv, float inv_em1) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = threshold_fn(in[i], thr, thr_inv, inv_em1);
+}
+
+inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace ssrs
+
+using namespace ssrs;
+
+// SSRS_STENCIL_PATH=plain|tma forces a staging path (tests); default: TMA when eligible.
+extern "C" int ssrs_updraft(const float* dem, int rows, int cols, float resolution, const float* wspeed,
+                            const float* wdirn, float uniform_wspeed, float uniform_wdirn_deg, float threshold,
+                            float* slope_deg, float* aspect_deg, float* orograph, float* updraft, void* stream) {
+    SSRS_REQUIRE(dem != nullptr, "ssrs_updraft: dem is NULL");
+    SSRS_REQUIRE(rows >= 3 && cols >= 3, "ssrs_updraft: grid %dx%d is smaller than the 3x3 stencil", rows, cols);
+    SSRS_REQUIRE(resolution > 0.0f, "ssrs_updraft: resolution must be positive");
+    SSRS_REQUIRE((wspeed == nullptr) == (wdirn == nullptr), "ssrs_updraft: wspeed and wdirn must both be given or both NULL");
+    SSRS_REQUIRE(threshold > 0.0f, "ssrs_updraft: threshold must be positive");
+    UpdraftParams p;
+    p.dem = dem; p.wspeed = wspeed; p.wdirn = wdirn;
+    p.slope = slope_deg; p.aspect = aspect_deg; p.orograph = orograph; p.updraft = updraft;
+    p.rows = rows; p.cols = cols;
+    p.tiles_r = (int)cdiv(rows, TH); p.tiles_c = (int)cdiv(cols, TW);
+    p.inv8res = 1.0f / (8.0f * resolution);
+    const double wd = (double)uniform_wdirn_deg * M_PI / 180.0;
+    p.uni_speed = uniform_wspeed; p.uni_sin = (float)sin(wd); p.uni_cos = (float)cos(wd);
+    p.thr = threshold; p.thr_inv = 1.0f / threshold; p.inv_em1 = (float)(1.0 / (exp(1.0) - 1.0));
+    p.vec_ok = (cols % 4 == 0) && aligned16(dem) && aligned16(wspeed) && aligned16(wdirn) && aligned16(slope_deg) &&
+               aligned16(aspect_deg) && aligned16(orograph) && aligned16(updraft);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ntiles = p.tiles_r * p.tiles_c;
+
+    const char* force = getenv("SSRS_STENCIL_PATH");
+    bool want_tma = p.vec_ok && ntiles > 1;
+    if (force && force[0] == 'p') want_tma = false;
+    if (force && force[0] == 't') {
+        SSRS_REQUIRE(p.vec_ok, "ssrs_updraft: SSRS_STENCIL_PATH=tma needs cols %% 4 == 0 and 16-byte aligned rasters");
+        want_tma = true;
+    }
+    if (want_tma) {
+        EncodeTiledFn enc = get_encode_fn();
+        if (enc == nullptr) {
+            set_error("ssrs_updraft: cuTensorMapEncodeTiled not available from the driver");
+            return SSRS_ERR_CUDA;
+        }
+        CUtensorMap map;
+        cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+        cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)SW, (cuuint32_t)SH};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dem), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("ssrs_updraft: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+            return SSRS_ERR_CUDA;
+        }
+        // persistent grid: a multiple of the SM count (3 CTAs/SM: 37 KB smem + 256 threads each)
+        int grid = sm_count() * 3;
+        if (grid > ntiles) grid = ntiles;
+        updraft_tma_kernel<true><<<grid, NTHREADS, 0, st>>>(p, map);
+    } else if (p.vec_ok) {
+        updraft_plain_kernel<true><<<ntiles, NTHREADS, 0, st>>>(p);
+    } else {
+        updraft_plain_kernel<false><<<ntiles, NTHREADS, 0, st>>>(p);
+    }
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int ssrs_threshold(const float* in, float* out, int64_t n, float threshold, void* stream) {
+    SSRS_REQUIRE(in != nullptr && out != nullptr, "ssrs_threshold: NULL raster");
+    SSRS_REQUIRE(n >= 0 && threshold > 0.0f, "ssrs_threshold: bad size or threshold");
+    if (n == 0) return SSRS_OK;
+    int64_t blocks = cdiv(n, 256);
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    threshold_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, n, threshold, 1.0f / threshold, (float)(1.0 / (exp(1.0) - 1.0)));
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}

@@ -1,0 +1,158 @@
+"""Stage 3+4 on the GPU (through the C-ABI) vs the reference's golden trajectories and the C oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle_c as OC
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["n0_m1", "n0_m3", "n0_m0", "d45_m1", "d270_m2", "n0_nu05", "n0_nu0"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_step_for_step(golden, name):
+    """Verification mode: the reference's pre-drawn uniforms -> identical positions at every step,
+    identical lengths, and bit-exact presence counts."""
+    from ssrs_b200 import movmodel as mm
+    g = golden("tracks")
+    dirn, mem, nu = g[f"{name}_params"]
+    lens = g[f"{name}_len"]
+    cap = g[f"{name}_traj"].shape[1]
+    starts = g[f"{name}_starts"]
+    res = mm.simulate_tracks_batch(float(dirn), starts[:, 0], starts[:, 1], g["U32"].shape, int(mem), float(nu),
+                                   updraft_field=g["U32"], potential_field=g["P32"], uniforms=g[f"{name}_uni"],
+                                   record=True, traj_cap=cap)
+    got_len = res.traj_len.cpu().numpy()
+    traj = res.traj.permute(1, 0, 2).cpu().numpy()
+    complete = lens <= cap
+    assert complete.any()
+    for t in np.flatnonzero(complete):
+        assert got_len[t] == lens[t]
+        assert np.array_equal(traj[t, :lens[t]], g[f"{name}_traj"][t, :lens[t]])
+    if complete.all():
+        assert np.array_equal(res.presence.cpu().numpy(), g[f"{name}_presence"].astype(np.int32))
+        assert res.total_steps == int((lens - 1).sum())
+        # compute_presence_counts from stored trajectories gives the same raster
+        assert np.array_equal(mm.compute_presence_counts(res.tracks(), g["U32"].shape), res.presence.cpu().numpy())
+
+
+def test_drw_and_serial_api(golden):
+    from ssrs_b200 import movmodel as mm
+    g = golden("tracks")
+    tj = g["drw_traj"]
+    res = mm.simulate_tracks_batch(30.0, [5], [30], g["U32"].shape, 1, 1.0, uniforms=g["drw_uni"][None, :], record=True,
+                                   traj_cap=len(tj) + 1)
+    assert np.array_equal(res.tracks()[0], tj)
+    # reference-signature call consuming numpy's global stream
+    name = "n0_m1"
+    t = 2
+    np.random.seed(1000 + t)
+    out = mm.generate_simulated_tracks(0.0, list(g[f"{name}_starts"][t]), g["U32"].shape, 1, 1.0, g["U32"], g["P32"])
+    L = int(g[f"{name}_len"][t])
+    assert out.dtype == np.int16 and np.array_equal(out, g[f"{name}_traj"][t, :L])
+    after = np.random.random_sample()
+    np.random.seed(1000 + t)
+    np.random.random_sample(L - 1)
+    assert after == np.random.random_sample()        # the global stream was advanced exactly like the reference
+
+
+def _fields(rows, cols, res, seed=1):
+    from ssrs_b200.synth import synthetic_dem
+    z = synthetic_dem(rows, cols, res, seed=seed)
+    _, _, _, K = O.updraft_pipeline(z, res, 10.0, 270.0, 0.75)
+    return K.astype(np.float32)
+
+
+@pytest.mark.parametrize("mem,nu,dirn", [(1, 1.0, 0.0), (2, 1.0, 315.0), (0, 1.0, 0.0), (1, 2.0, 90.0)])
+def test_philox_matches_c_oracle(mem, nu, dirn):
+    """Production mode: Philox streams keyed by (seed, track id, step) -> the C oracle reproduces every
+    trajectory and the presence raster bit for bit (3000 tracks on a 200x240 grid)."""
+    from ssrs_b200 import movmodel as mm
+    rows, cols = 200, 240
+    U = _fields(rows, cols, 100.0)
+    P = O.solve_potential(U.astype(np.float64), dirn)
+    rng = np.random.RandomState(3)
+    n = 3000
+    starts = np.stack([rng.randint(2, 30, n), rng.randint(2, cols - 2, n)], 1).astype(np.int32)
+    cap = 4 * max(rows, cols)
+    ref = OC.step_tracks(U, P, (rows, cols), starts, dirn, mem, nu, seed=1234, track_id0=17, traj_cap=cap, nthreads=8)
+    res = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, updraft_field=U,
+                                   potential_field=P, seed=1234, track_id0=17, record=True, traj_cap=cap)
+    assert res.total_steps == ref["total_steps"]
+    assert np.array_equal(res.traj_len.cpu().numpy(), ref["traj_len"])
+    assert np.array_equal(res.presence.cpu().numpy(), ref["presence"])
+    traj = res.traj.permute(1, 0, 2).cpu().numpy()
+    for t in range(0, n, 37):
+        L = min(ref["traj_len"][t], cap)
+        assert np.array_equal(traj[t, :L], ref["traj"][t, :L])
+
+
+def test_sharding_invariance():
+    """Tracks block-partitioned over 1/2/4/8 shards (what each GPU of a box would run) give bit-identical
+    summed presence and per-track lengths: the RNG is keyed by the global track id."""
+    from ssrs_b200 import movmodel as mm
+    rows, cols = 200, 240
+    U = _fields(rows, cols, 100.0, seed=2)
+    P = O.solve_potential(U.astype(np.float64), 0.0)
+    f = mm.interleave_fields(U, P)
+    rng = np.random.RandomState(5)
+    n = 4096
+    sr, sc = rng.randint(2, 30, n), rng.randint(2, cols - 2, n)
+    whole = mm.simulate_tracks_batch(0.0, sr, sc, (rows, cols), fields=f, seed=7)
+    base_p, base_l = whole.presence.cpu().numpy(), whole.traj_len.cpu().numpy()
+    for shards in (2, 4, 8):
+        pres, lens = None, []
+        per = n // shards
+        for s in range(shards):
+            sl = slice(s * per, (s + 1) * per)
+            r = mm.simulate_tracks_batch(0.0, sr[sl], sc[sl], (rows, cols), fields=f, seed=7, track_id0=s * per,
+                                         presence=pres)
+            pres = r.presence
+            lens.append(r.traj_len.cpu().numpy())
+        assert np.array_equal(pres.cpu().numpy(), base_p)
+        assert np.array_equal(np.concatenate(lens), base_l)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape: 100k tracks on a (5000, 6000) grid.  Properties that do not need the
+    oracle at full size: sum(presence) == total_steps + n_tracks (every appended point is counted once);
+    a 512-track sample reproduces the C oracle exactly; every track ends on the border or at max_moves."""
+    import torch
+    from ssrs_b200 import layers, movmodel as mm
+    from ssrs_b200.synth import synthetic_dem
+    rows, cols, res = 5000, 6000, 10.0
+    z = torch.from_numpy(synthetic_dem(rows, cols, res)).cuda()
+    up = layers.updraft_fields(z, res, 10.0, 270.0, 0.75, want=("updraft",))["updraft"]
+    # a smooth stand-in potential (north = 0, south = 1000 plus relief); stage 2 has its own tests
+    yy = torch.linspace(1000.0, 0.0, rows, device="cuda")[:, None]
+    pot = (yy + 5.0 * torch.sin(torch.arange(cols, device="cuda")[None, :] / 97.0)).float().contiguous()
+    f = mm.interleave_fields(up, pot)
+    n = 100_000
+    rng = np.random.RandomState(1)
+    sr, sc = rng.randint(99, 200, n), rng.randint(506, 5489, n)
+    res_gpu = mm.simulate_tracks_batch(0.0, sr, sc, (rows, cols), fields=f, seed=99)
+    total = res_gpu.total_steps
+    assert int(res_gpu.presence.sum(dtype=torch.int64).item()) == total + n
+    lens = res_gpu.traj_len.cpu().numpy()
+    assert lens.min() > 500 and total == int((lens.astype(np.int64) - 1).sum())
+    m = 512
+    ref = OC.step_tracks(up.cpu().numpy(), pot.cpu().numpy(), (rows, cols), np.stack([sr[:m], sc[:m]], 1), 0.0, 1, 1.0,
+                         seed=99, want_presence=False, nthreads=8)
+    assert np.array_equal(lens[:m], ref["traj_len"])
+
+
+def test_errors():
+    from ssrs_b200 import movmodel as mm
+    from ssrs_b200._native import NativeError
+    U = np.ones((50, 60), np.float32)
+    with pytest.raises(ValueError):
+        mm.simulate_tracks_batch(0.0, [70], [5], (50, 60), updraft_field=U, potential_field=U)
+    with pytest.raises(NativeError):
+        mm.simulate_tracks_batch(0.0, [7], [5], (50, 60), memory_parameter=99, updraft_field=U, potential_field=U)
+    with pytest.raises(ValueError):
+        mm.get_starting_indices(10, (60, 5, 1, 2), "random", (60., 50.), 100.)
+    with pytest.raises(ValueError):
+        mm.get_starting_indices(10, (5, 55, 1, 2), "spiral", (60., 50.), 100.)
+    r = mm.simulate_tracks_batch(0.0, [], [], (50, 60), updraft_field=U, potential_field=U)
+    assert r.total_steps == 0 and int(r.presence.sum()) == 0

@@ -1,0 +1,107 @@
+"""CPU tests of the product's host logic and of the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssrs_b200 import build, _native
+    lib_path = build.build()
+    header = open(os.path.join(ROOT, "include", "ssrs_b200.h")).read()
+    declared = set(re.findall(r"SSRS_API\s+[\w\s\*]+?\b(ssrs_\w+)\s*\(", header))
+    assert declared and declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.ssrs_abi_version.restype = ctypes.c_int
+    assert lib.ssrs_abi_version() == 1
+    _native.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ssrs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src.replace("`/root/reference", "").replace("(`/root/reference", "") \
+                    or f.endswith(".py"), f
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ssrs_b200 import layers, _native
+    with pytest.raises(_native.NativeError):
+        layers.compute_slope_degrees(np.zeros((8, 8), np.float32), 10.0)
+
+
+def test_config_contract():
+    from ssrs_b200 import Config
+    c = Config()
+    names = [f.name for f in dataclasses.fields(c)]
+    assert len(names) == 34 and names[0] == "run_name" and names[-1] == "fig_dpi"
+    assert c.updraft_threshold == 0.75 and c.track_dirn_restrict == 1 and c.track_start_region == (5, 55, 1, 2)
+    assert c.turbine_mrkr_styles[0] == "1k"
+    s = str(c)
+    assert ":::: Simulating tracks\nmovement_model = fluidflow" in s       # the reference's positional section break
+    c2 = dataclasses.replace(c, track_count=5, sim_mode="snapshot")
+    assert c2.track_count == 5 and c.track_count == 1000
+
+
+def test_host_helpers_against_golden(golden):
+    from ssrs_b200 import movmodel as mm
+    g = golden("tables")
+    for i in range(9):
+        assert np.array_equal(mm.get_track_restrictions(i // 3 - 1, i % 3 - 1), g["masks"][i])
+    for th, w in zip(g["thetas"], g["dirw"]):
+        assert np.array_equal(mm.get_directional_probs(th * np.pi / 180.0), w)
+    assert np.array_equal(mm.neighbour_delta_norms_inv, g["norms_inv"])
+    assert np.array_equal(np.array(mm.neighbour_deltas), g["deltas"])
+    for th in (0, 30, 45, 90, 180, 270, 315, -45):
+        for shp in ((23, 31), (60, 50)):
+            bn, be = mm.MovModel(th, shp).get_boundary_nodes()
+            assert np.array_equal(bn, g[f"bn_{th}_{shp[0]}x{shp[1]}"]) and np.array_equal(be, g[f"be_{th}_{shp[0]}x{shp[1]}"])
+    np.random.seed(4)
+    r, c = mm.get_starting_indices(64, (5, 55, 1, 2), "random", (60., 50.), 100.)
+    assert np.array_equal(r, g["start_random_rows"]) and np.array_equal(c, g["start_random_cols"])
+    r, c = mm.get_starting_indices(37, (5, 55, 1, 2), "structured", (60., 50.), 100.)
+    assert np.array_equal(r, g["start_struct_rows"]) and np.array_equal(c, g["start_struct_cols"])
+    with pytest.raises(ValueError):
+        mm.get_starting_indices(10, (60, 5, 1, 2), "random", (60., 50.), 100.)
+    with pytest.raises(ValueError):
+        mm.get_starting_indices(10, (5, 55, 1, 2), "spiral", (60., 50.), 100.)
+    assert mm.move_away_from_boundary(0, 0, 50, 60) == (2, 2)
+    assert mm.move_away_from_boundary(1, 1, 50, 60) == (3, 1)          # row <= 1 but col <= 0: asymmetric
+    assert mm.move_away_from_boundary(48, 58, 50, 60) == (46, 56)
+    assert mm.harmonic_mean(0.0, 3.0, 1e-8) == 1e-8 and mm.harmonic_mean(1.0, 3.0) == 1.5
+
+
+def test_assemble_matches_oracle_operator():
+    """MovModel.assemble_sparse_linear_system (API parity) encodes the same links as the oracle's operator,
+    including the last-column S/SW factor swap."""
+    from oracle import oracle_np as O
+    from ssrs_b200 import movmodel as mm
+    nrow, ncol = 9, 7
+    ri, ci, fa = mm.MovModel(0.0, (nrow, ncol)).assemble_sparse_linear_system()
+    assert ri.dtype == np.uint32 and fa.dtype == np.float32
+    K = np.ones((nrow, ncol))
+    g = O.edge_weights(K)
+    dense = np.zeros((nrow * ncol, nrow * ncol))
+    dense[ri, ci] = 1.0 / fa.astype(np.float64)
+    for d in range(9):
+        dr, dc = d // 3 - 1, d % 3 - 1
+        for r in range(nrow):
+            for c in range(ncol):
+                if d == 4 or not (0 <= r + dr < nrow and 0 <= c + dc < ncol):
+                    continue
+                i, j = c * nrow + r, (c + dc) * nrow + (r + dr)
+                assert dense[i, j] == g[d, r, c], (r, c, dr, dc)
