@@ -31,6 +31,8 @@ constexpr int SH = TH + 2;            // 34 staged rows
 constexpr int NTHREADS = 256;
 constexpr int STAGES = 2;
 constexpr uint32_t TILE_BYTES = SW * SH * sizeof(float);
+// each TMA destination must be 128-byte aligned: pad the per-stage stride
+constexpr int TILE_STRIDE = ((SW * SH + 31) / 32) * 32;
 
 struct UpdraftParams {
     const float* dem;
@@ -213,7 +215,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 template <bool VEC>
 __global__ void __launch_bounds__(NTHREADS) updraft_tma_kernel(const UpdraftParams p,
                                                                const __grid_constant__ CUtensorMap dem_map) {
-    __shared__ __align__(128) float tiles[STAGES][SH * SW];
+    __shared__ __align__(128) float tiles[STAGES][TILE_STRIDE];
     __shared__ __align__(8) uint64_t full[STAGES];
     const int ntiles = p.tiles_r * p.tiles_c;
     if (threadIdx.x == 0) {
