@@ -1,0 +1,178 @@
+// Data-parallel primitives used by the potential solver (stage 2).
+//
+// Every solver kernel is written once as a `__host__ __device__` lambda over an index range and launched
+// through pfor()/preduce().  The product build runs them as CUDA kernels on sm_100a.  Compiling the same
+// translation unit with -DSSRS_HOST_EMU turns pfor() into a serial host loop: that build is TEST
+// INFRASTRUCTURE ONLY (tests/hostemu.py builds it into tests/_build/, `-m "not gpu"` tests use it to check
+// the solver's logic on CPU); nothing in ssrs_b200/ ever loads it, and the product library contains no
+// host execution path.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#ifndef SSRS_HOST_EMU
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#endif
+
+namespace ssrs {
+namespace par {
+
+#ifdef SSRS_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+#define SSRS_HD
+typedef void* stream_t;
+
+inline int dev_alloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
+inline void dev_free(void* p) { free(p); }
+inline int dev_zero(void* p, size_t bytes, stream_t) { memset(p, 0, bytes); return 0; }
+inline int dev_fill_byte(void* p, int v, size_t bytes, stream_t) { memset(p, v, bytes); return 0; }
+inline int copy_d2d(void* d, const void* s, size_t bytes, stream_t) { memcpy(d, s, bytes); return 0; }
+inline int copy_h2d(void* d, const void* s, size_t bytes, stream_t) { memcpy(d, s, bytes); return 0; }
+inline int copy_d2h(void* d, const void* s, size_t bytes, stream_t) { memcpy(d, s, bytes); return 0; }
+inline int sync(stream_t) { return 0; }
+
+template <class F>
+inline int pfor(int64_t n, stream_t, F f) {
+    for (int64_t i = 0; i < n; ++i) f(i);
+    return 0;
+}
+template <class F>
+inline int preduce_sum(int64_t n, stream_t, double* out, F f) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += f(i);
+    *out = s;
+    return 0;
+}
+template <class F>
+inline int preduce_sum2(int64_t n, stream_t, double* out0, double* out1, F f) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = 0; i < n; ++i) { double a, b; f(i, a, b); s0 += a; s1 += b; }
+    *out0 = s0; *out1 = s1;
+    return 0;
+}
+inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t) {
+    int64_t run = 0;
+    for (int64_t i = 0; i < n; ++i) { int64_t v = data[i]; data[i] = run; run += v; }
+    *total = run;
+    return 0;
+}
+inline int atomic_add_int(int* p, int v) { int o = *p; *p = o + v; return o; }
+
+#else
+// ------------------------------------------------------------------------------------------------
+#define SSRS_HD __host__ __device__
+typedef cudaStream_t stream_t;
+
+inline int dev_alloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline int dev_zero(void* p, size_t bytes, stream_t s) { return cudaMemsetAsync(p, 0, bytes, s) == cudaSuccess ? 0 : -1; }
+inline int dev_fill_byte(void* p, int v, size_t bytes, stream_t s) { return cudaMemsetAsync(p, v, bytes, s) == cudaSuccess ? 0 : -1; }
+inline int copy_d2d(void* d, const void* s, size_t b, stream_t st) { return cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : -1; }
+inline int copy_h2d(void* d, const void* s, size_t b, stream_t st) { return cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -1; }
+inline int copy_d2h(void* d, const void* s, size_t b, stream_t st) { return cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st) == cudaSuccess ? 0 : -1; }
+inline int sync(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+
+int grid_cap();     // SM count x 8 (defined in potential.cu)
+
+template <class F>
+__global__ void __launch_bounds__(256) pfor_kernel(int64_t n, F f) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+template <class F>
+inline int pfor(int64_t n, stream_t s, F f) {
+    if (n <= 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > grid_cap()) blocks = grid_cap();
+    pfor_kernel<<<(int)blocks, 256, 0, s>>>(n, f);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+constexpr int RED_BLOCKS = 1024;
+double* reduce_scratch();       // device buffer of 2*RED_BLOCKS+2 doubles (defined in potential.cu)
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[8];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = (threadIdx.x < 8) ? sh[threadIdx.x] : 0.0;
+    if (threadIdx.x < 32)
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    return t;   // valid in thread 0
+}
+template <class F>
+__global__ void __launch_bounds__(256) reduce2_kernel(int64_t n, double* partial, F f) {
+    double s0 = 0.0, s1 = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a, b;
+        f(i, a, b);
+        s0 += a; s1 += b;
+    }
+    s0 = block_sum(s0);
+    s1 = block_sum(s1);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s0; partial[RED_BLOCKS + blockIdx.x] = s1; }
+}
+__global__ void __launch_bounds__(256) reduce_final_kernel(const double* partial, int nb, double* out) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) { s0 += partial[i]; s1 += partial[RED_BLOCKS + i]; }
+    s0 = block_sum(s0);
+    s1 = block_sum(s1);
+    if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
+}
+// Deterministic two-stage reductions (fixed grid, fixed tree); the result is read back (stream sync).
+template <class F>
+inline int preduce_sum2(int64_t n, stream_t s, double* out0, double* out1, F f) {
+    double* scratch = reduce_scratch();
+    if (!scratch) return -1;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    reduce2_kernel<<<(int)blocks, 256, 0, s>>>(n, scratch, f);
+    reduce_final_kernel<<<1, 256, 0, s>>>(scratch, (int)blocks, scratch + 2 * RED_BLOCKS);
+    double h[2];
+    if (cudaMemcpyAsync(h, scratch + 2 * RED_BLOCKS, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+    *out0 = h[0]; *out1 = h[1];
+    return 0;
+}
+template <class F>
+inline int preduce_sum(int64_t n, stream_t s, double* out, F f) {
+    double dummy;
+    return preduce_sum2(n, s, out, &dummy, [=] __host__ __device__(int64_t i, double& a, double& b) { a = f(i); b = 0.0; });
+}
+inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t s) {
+    if (n <= 0) { *total = 0; return 0; }
+    int64_t last_in = 0, last_out = 0;
+    if (cudaMemcpyAsync(&last_in, data + n - 1, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    size_t tmp_bytes = 0;
+    if (cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, data, data, n, s) != cudaSuccess) return -1;
+    void* tmp = nullptr;
+    if (cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) return -1;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, data, data, n, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_out, data + n - 1, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return -1;
+    *total = last_in + last_out;
+    return 0;
+}
+__device__ __forceinline__ int atomic_add_int_dev(int* p, int v) { return atomicAdd(p, v); }
+__host__ __device__ __forceinline__ int atomic_add_int(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    int o = *p; *p = o + v; return o;
+#endif
+}
+#endif
+
+}  // namespace par
+}  // namespace ssrs
