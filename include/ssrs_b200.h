@@ -70,6 +70,36 @@ SSRS_API int ssrs_updraft(const float* dem, int rows, int cols, float resolution
 SSRS_API int ssrs_threshold(const float* in, float* out, int64_t n, float threshold, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stage 2 — directional potential.  Replaces
+ *   MovModel.assemble_sparse_linear_system   ssrs/movmodel.py:59-84   (the operator is built into the kernels)
+ *   MovModel.solve_sparse_linear_system      ssrs/movmodel.py:86-128  (SuperLU -> matrix-free AMG + BiCGStab)
+ * conductivity: float32 [rows][cols] thresholded updraft (the `conductivity` argument of the reference).
+ * bnodes_host / bvalues_host: HOST arrays exactly as MovModel.get_boundary_nodes() returns them
+ *   (ssrs/movmodel.py:21-57): column-major node ids `col*rows + row` and their Dirichlet values.
+ * rtol: relative 2-norm residual of the un-normalised system (<= 0 -> 1e-9); max_iter <= 0 -> 300.
+ * potential: float32 [rows][cols] out (the reference returns float32, :128).
+ * Allocates its workspace internally (cudaMalloc) and frees it before returning; synchronous.
+ * Returns SSRS_ERR_NOT_CONVERGED (potential still written) if the tolerance was not reached.
+ */
+typedef struct ssrs_solve_stats {
+    int32_t iterations;          /* BiCGStab iterations (two V-cycles + two operator applications each) */
+    int32_t restarts;            /* true-residual restarts */
+    int32_t levels;              /* AMG levels including the fine grid */
+    int32_t converged;           /* 1: tolerance met; 2: stopped at the float64 attainable accuracy (true residual stagnated <= 1e-6) */
+    double rel_residual;         /* final |b - A x|_2 / |b - A x0|_2, true residual */
+    double setup_ms, solve_ms;   /* host wall clock around the synchronous phases */
+    double operator_complexity;  /* sum of nnz over levels / fine nnz */
+    int64_t level_rows[24];
+    int64_t coarsest_rows;
+    int64_t workspace_bytes;
+} ssrs_solve_stats;
+
+SSRS_API int ssrs_potential_solve(const float* conductivity, int rows, int cols,
+                                  const int64_t* bnodes_host, const double* bvalues_host, int64_t n_bnodes,
+                                  double rtol, int max_iter, float* potential, ssrs_solve_stats* stats,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage 3+4 — batched track stepping with fused presence accumulation.  Replaces
  *   generate_simulated_tracks  ssrs/movmodel.py:264-318  (one call per track in the reference,
  *                              mapped over a process pool at ssrs/simulator.py:360-369)

@@ -19,6 +19,8 @@ EXPORTS = {
     "ssrs_updraft": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "ssrs_potential_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int64,
+                                       C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_step_tracks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                    C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -144,9 +144,14 @@ inline int preduce_sum2(int64_t n, stream_t s, double* out0, double* out1, F f) 
     return 0;
 }
 template <class F>
+struct OneOfTwo {
+    F f;
+    __host__ __device__ void operator()(int64_t i, double& a, double& b) const { a = f(i); b = 0.0; }
+};
+template <class F>
 inline int preduce_sum(int64_t n, stream_t s, double* out, F f) {
     double dummy;
-    return preduce_sum2(n, s, out, &dummy, [=] __host__ __device__(int64_t i, double& a, double& b) { a = f(i); b = 0.0; });
+    return preduce_sum2(n, s, out, &dummy, OneOfTwo<F>{f});
 }
 inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t s) {
     if (n <= 0) { *total = 0; return 0; }
@@ -164,7 +169,6 @@ inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t
     *total = last_in + last_out;
     return 0;
 }
-__device__ __forceinline__ int atomic_add_int_dev(int* p, int v) { return atomicAdd(p, v); }
 __host__ __device__ __forceinline__ int atomic_add_int(int* p, int v) {
 #ifdef __CUDA_ARCH__
     return atomicAdd(p, v);

@@ -1,0 +1,49 @@
+"""CPU check of the stage-2 solver's logic: ssrs_b200/csrc/potential.cu compiled with -DSSRS_HOST_EMU
+(tests/hostemu.py) against the reference's golden potentials and the oracle's direct solve."""
+import numpy as np
+import pytest
+
+import hostemu
+from oracle import oracle_np as O
+
+ULP = float(np.spacing(np.float32(1000.0)))
+
+
+@pytest.mark.parametrize("key,dirs", [("rand", (0, 90, 180, 270, 45, -45, 30)), ("dem", (0, 270, 45)), ("dem2", (0,))])
+def test_golden_potentials(golden, key, dirs):
+    g = golden("potential")
+    K = g[f"{key}_K"]
+    for th in dirs:
+        bn, bv = O.boundary_nodes(th, *K.shape)
+        rc, phi, st, err = hostemu.solve(K, bn, bv)
+        assert rc == 0, err
+        assert st.converged in (1, 2) and st.rel_residual < 1e-6
+        ref = g[f"{key}_phi_{th}"].astype(np.float64)
+        # contract 1e-5 relative (=1e-2); engineering target: within ~1 float32 ulp of the direct solve
+        assert np.abs(phi.astype(np.float64) - ref).max() <= 1.5 * ULP, th
+        mask, val = O.boundary_grid(th, *K.shape)
+        assert np.array_equal(phi[mask], val[mask].astype(np.float32))
+
+
+def test_maximum_principle_and_hierarchy():
+    rng = np.random.RandomState(0)
+    K = (rng.rand(90, 70) * (rng.rand(90, 70) > 0.5)).astype(np.float32)
+    K[20:40, 10:50] = 0.9          # a conducting island
+    K[19, 9:51] = 1e-9             # wrapped in a film that conducts less than the zero cells
+    bn, bv = O.boundary_nodes(0.0, *K.shape)
+    rc, phi, st, err = hostemu.solve(K, bn, bv)
+    assert rc == 0, err
+    assert phi.min() >= 0.0 and phi.max() <= 1000.0
+    rows = list(st.level_rows[:st.levels])
+    assert st.levels >= 3 and all(rows[i + 1] < rows[i] for i in range(len(rows) - 1))
+    assert st.operator_complexity < 2.5
+    ref = O.solve_potential(K.astype(np.float64), 0.0)
+    assert np.abs(phi.astype(np.float64) - ref).max() <= 2 * ULP
+
+
+def test_bad_arguments():
+    K = np.ones((10, 10), np.float32)
+    rc, *_ = hostemu.solve(K, np.array([], dtype=np.int64), np.array([]))
+    assert rc == -1
+    rc, *_ = hostemu.solve(K, np.array([1000]), np.array([0.0]))
+    assert rc == -1
