@@ -138,6 +138,12 @@ SSRS_API int ssrs_interleave_fields(const float* updraft, const float* potential
 SSRS_API int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len,
                          int64_t n_tracks, int rows, int cols, uint32_t* presence, void* stream);
 
+/* compute_smooth_presence_counts (ssrs/movmodel.py:422-439): disk kernel of `radius` cells, zero padding
+ * ('same'), normalised by the kernel's cell count.  row_prefix: int64 [rows][cols+1] running sums of the
+ * counts along each row (row_prefix[r][c] = sum counts[r][0..c-1]); out: float32 [rows][cols]. */
+SSRS_API int ssrs_smooth_presence(const long long* row_prefix, int rows, int cols, int radius, float* out,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,329 @@
+"""`Simulator` — drop-in for the hot path of `/root/reference/ssrs/simulator.py` (class Simulator(Config)).
+
+Same constructor shape (`Simulator(in_config=None, **kwargs)`), attribute surface, method
+names, case/ID strings and on-disk artefacts (`<case>_orograph.npy` f32, `<id>_potential.npy` f32,
+`<id>_tracks.pkl`, `summary_presence.npy` f32) as the reference; the bodies that call stages 1-4 run on the GPU:
+
+    reference                                           here
+    compute_orographic_updraft_uniform   :189-198       one fused stencil kernel (ssrs_updraft)
+    compute_orographic_updrafts_using_wtk :200-215      same kernel with per-cell wind rasters
+    load_updrafts                        :230-243       threshold on the GPU (ssrs_threshold)
+    get_directional_potential            :259-288       matrix-free AMG/BiCGStab solve (ssrs_potential_solve)
+    simulate_tracks                      :332-386       one batched launch (ssrs_step_tracks) instead of mp.Pool
+    plot_presence_map (data part)        :508-546       compute_presence_map(): counts fused into the stepper
+
+Out of scope: terrain/WTK/turbine downloads, CRS handling and matplotlib plotting.  The reference
+constructor always downloads terrain; here it is injected with keyword-only extensions:
+    elevation=   float raster [rows=north, cols=east] matching `gridsize`
+    wind_cases=  {case_id: (wspeed, wdirn)} rasters or scalars for snapshot/seasonal modes (stands in for WTK)
+    bounds=      projected bounds (west, south, east, north); default puts the south-west corner at (0, 0)
+When `torch.distributed` is initialised, tracks are block-partitioned by global id over the ranks, fields are
+replicated and presence maps are summed with one all-reduce (NCCL on GPUs).
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+import time
+from dataclasses import asdict
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _native as N
+from . import dist as _dist
+from .config import Config
+from .layers import get_above_threshold_speed, updraft_fields
+from .movmodel import MovModel, get_starting_indices, interleave_fields, simulate_tracks_batch
+from .potential import solve_potential_device
+
+TRACKS_PKL_LIMIT = 50_000      # above this the pickled list-of-arrays format is impractical; a packed .npz is written
+
+
+def _elapsed(t0: float) -> str:
+    s = time.time() - t0
+    return f"{int(s // 60)} min {int(s % 60)} sec" if s >= 60 else f"{s:.2f} sec"
+
+
+class Simulator(Config):
+    """ Class for SSRS simulation """
+
+    lonlat_crs = 'EPSG:4326'
+    time_format = 'y%Ym%md%dh%H'
+
+    def __init__(self, in_config: Config = None, *, elevation=None, wind_cases: Optional[Dict] = None,
+                 bounds=None, **kwargs) -> None:
+        if in_config is None:
+            super().__init__(**kwargs)
+        else:
+            super().__init__(**asdict(in_config))
+        N.load()                 # no CUDA library -> fail here, loudly
+        print(f'\n---- SSRS in {self.sim_mode} mode')
+        print(f'Run name: {self.run_name}')
+        if self.sim_seed >= 0:                                   # reference :50-52
+            print('Specified random number seed:', self.sim_seed)
+            np.random.seed(self.sim_seed)
+
+        print(f'Output dir: {os.path.join(self.out_dir, self.run_name)}')
+        self.data_dir = os.path.join(self.out_dir, self.run_name, 'data/')
+        self.fig_dir = os.path.join(self.out_dir, self.run_name, 'figs/')
+        self.mode_data_dir = os.path.join(self.data_dir, self.sim_mode)
+        self.mode_fig_dir = os.path.join(self.fig_dir, self.sim_mode)
+        for d in (self.mode_data_dir, self.mode_fig_dir):
+            os.makedirs(d, exist_ok=True)
+        # same JSON dump of the configuration as the reference (:63-67); arrays are attached afterwards
+        with open(os.path.join(self.out_dir, self.run_name, f'{self.run_name}.json'), 'w', encoding='utf-8') as f:
+            json.dump(self.__dict__, f, ensure_ascii=False, indent=2)
+
+        print(f'Terrain resolution = {self.resolution} m')
+        xsize = int(round((self.region_width_km[0] * 1000. / self.resolution)))
+        ysize = int(round((self.region_width_km[1] * 1000. / self.resolution)))
+        self.gridsize = (ysize, xsize)
+        print(f'Terrain grid size = {self.gridsize}')
+        if bounds is None:
+            bounds = (0.0, 0.0, (xsize - 1) * self.resolution, (ysize - 1) * self.resolution)
+        self.bounds = tuple(bounds)
+        self.extent = (self.bounds[0], self.bounds[2], self.bounds[1], self.bounds[3])
+        self.lonlat_bounds = None            # needs PROJ; not on the hot path
+        self.terrain_layers = {'Elevation': 'injected'}
+        self.turbines = None
+        self.region = None
+        if elevation is None:
+            raise ValueError("ssrs_b200.Simulator needs elevation= (terrain download is outside the hot path; "
+                             "inject the DEM raster [rows=north, cols=east])")
+        torch = N.require_cuda()
+        if isinstance(elevation, torch.Tensor):
+            z = elevation.to(device="cuda", dtype=torch.float32).contiguous()
+        else:
+            z = torch.from_numpy(np.ascontiguousarray(elevation, dtype=np.float32)).to("cuda")
+        if tuple(z.shape) != self.gridsize:
+            raise ValueError(f"elevation shape {tuple(z.shape)} does not match gridsize {self.gridsize}")
+        self._elev = z
+        self._presence: Dict[str, "torch.Tensor"] = {}
+        self._track_results = {}
+        self.timings: Dict[str, float] = {}
+
+        mode = self.sim_mode.lower()
+        if mode != 'uniform':
+            if not wind_cases:
+                raise ValueError(f"sim_mode={self.sim_mode!r} needs wind_cases= (WTK download is outside the hot path)")
+            self.case_ids = list(wind_cases.keys())
+            self._wind_cases = wind_cases
+            self.compute_orographic_updrafts_using_wtk()
+        else:
+            print(f'Uniform mode: Wind speed = {self.uniform_windspeed} m/s')
+            print(f'Uniform mode: Wind dirn = {self.uniform_winddirn} deg(cw)')
+            self.case_ids = [self._get_uniform_id()]
+            self.compute_orographic_updraft_uniform()
+        for case_id in self.case_ids:
+            self.compute_thermal_updrafts(case_id)
+        fig_aspect = self.region_width_km[0] / self.region_width_km[1]
+        self.fig_size = (self.fig_height * fig_aspect, self.fig_height)
+        self.km_bar = min([1, 5, 10], key=lambda x: abs(x - self.region_width_km[0] // 4))
+        print('SSRS Simulator initiation done.')
+
+    # ---------------------------------------------------------------- terrain
+    def get_terrain_elevation(self):
+        return self._elev.cpu().numpy()
+
+    def get_terrain_slope(self):
+        return updraft_fields(self._elev, self.resolution, 0.0, 0.0, want=("slope",))["slope"].cpu().numpy()
+
+    def get_terrain_aspect(self):
+        return updraft_fields(self._elev, self.resolution, 0.0, 0.0, want=("aspect",))["aspect"].cpu().numpy()
+
+    def get_terrain_layer(self, lname: str):
+        return {'Elevation': self.get_terrain_elevation, 'Slope': self.get_terrain_slope,
+                'Aspect': self.get_terrain_aspect}[lname]()
+
+    def get_terrain_grid(self):
+        xgrid = np.linspace(self.bounds[0], self.bounds[0] + (self.gridsize[1] - 1) * self.resolution, self.gridsize[1])
+        ygrid = np.linspace(self.bounds[1], self.bounds[1] + (self.gridsize[0] - 1) * self.resolution, self.gridsize[0])
+        return xgrid, ygrid
+
+    # ---------------------------------------------------------------- stage 1
+    def _save_orograph(self, case_id, orograph):
+        if _dist.rank() == 0:
+            np.save(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy', orograph.cpu().numpy())
+        _dist.barrier()
+
+    def compute_orographic_updraft_uniform(self) -> None:
+        print('Computing orographic updrafts..')
+        t0 = time.time()
+        out = updraft_fields(self._elev, self.resolution, float(self.uniform_windspeed), float(self.uniform_winddirn),
+                             self.updraft_threshold, want=("orograph",))
+        self.timings['updraft_s'] = time.time() - t0
+        self._save_orograph(self.case_ids[0], out["orograph"])
+
+    def compute_orographic_updrafts_using_wtk(self) -> None:
+        print('Computing orographic updrafts..', end="")
+        t0 = time.time()
+        for case_id in self.case_ids:
+            ws, wd = self._wind_cases[case_id]
+            out = updraft_fields(self._elev, self.resolution, ws, wd, self.updraft_threshold, want=("orograph",))
+            self._save_orograph(case_id, out["orograph"])
+        print(f'took {_elapsed(t0)}', flush=True)
+
+    def compute_thermal_updrafts(self, case_id: str):
+        if self.thermals_realization_count > 0:
+            raise NotImplementedError("thermal realisations are outside the B200 hot path (SURVEY.md §8f-3)")
+        print('No thermals requested!', flush=True)
+
+    def load_updrafts(self, case_id: str, apply_threshold=True):
+        """List with the (thresholded) orographic updraft, float32 numpy (reference :230-243)."""
+        oro = np.load(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy')
+        if apply_threshold:
+            return [get_above_threshold_speed(oro, self.updraft_threshold)]
+        return [oro]
+
+    def _load_updraft_device(self, case_id):
+        torch = N.require_cuda()
+        oro = torch.from_numpy(np.load(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy')).to("cuda")
+        return get_above_threshold_speed(oro, self.updraft_threshold)
+
+    def _get_orograph_fname(self, case_id: str, dirname: str = './'):
+        return os.path.join(dirname, f'{case_id}_orograph')
+
+    def _get_thermal_fname(self, case_id: str, real_id: int, dirname: str = './'):
+        return os.path.join(dirname, f'{case_id}_r{real_id}_thermals')
+
+    # ---------------------------------------------------------------- stage 2
+    def get_directional_potential(self, updraft, case_id, real_id):
+        """float32 potential for (case, realisation); cached as `<id>_potential.npy` like the reference
+        (:259-288, including its cache rules).  `updraft` may be numpy or a CUDA tensor."""
+        torch = N.require_cuda()
+        fname = self._get_potential_fname(case_id, real_id, self.mode_data_dir)
+        id_str = self._get_id_string(case_id, real_id)
+        try:
+            potential = np.load(f'{fname}.npy')
+            if potential.shape != self.gridsize:
+                raise FileNotFoundError
+            if (self.sim_seed < 0) & (real_id != 0):
+                raise FileNotFoundError
+            print(f'{id_str}: Found saved potential')
+            pot_dev = torch.from_numpy(potential).to("cuda")
+        except FileNotFoundError:
+            t0 = time.time()
+            print(f'{id_str}: Computing potential..', end="", flush=True)
+            pot_dev, stats = solve_potential_device(updraft, self.track_direction, strict=False)
+            self.timings['potential_s'] = time.time() - t0
+            self.solve_stats = stats
+            print(f'took {_elapsed(t0)}', flush=True)
+            potential = pot_dev.cpu().numpy()
+            if _dist.rank() == 0:
+                np.save(f'{fname}.npy', potential)
+            _dist.barrier()
+        if np.isnan(potential).any():
+            print('NANs found in potential!')
+        self._last_potential_device = pot_dev
+        return potential
+
+    def _get_id_string(self, case_id: str, real_id: Optional[int] = None):
+        out = f'{case_id}_d{int(self.track_direction % 360)}_t{int(self.updraft_threshold * 100)}_{self.movement_model}'
+        if real_id is not None:
+            out += f'_r{int(real_id)}'
+        return out
+
+    def _get_potential_fname(self, case_id: str, real_id: int, dirname: str):
+        return os.path.join(dirname, f'{self._get_id_string(case_id, real_id)}_potential')
+
+    # ---------------------------------------------------------------- stage 3 + 4
+    def _track_seed(self, case_index: int, real_id: int) -> int:
+        base = self.sim_seed if self.sim_seed >= 0 else int.from_bytes(os.urandom(4), 'little')
+        return (base * 1_000_003 + case_index * 1009 + real_id) & (2 ** 63 - 1)
+
+    def simulate_tracks(self, save_tracks: Optional[bool] = None):
+        """Simulate tracks (reference :332-386).  Presence counts are accumulated on the device during
+        stepping and kept per (case, realisation) in `self.presence_counts(id)`."""
+        torch = N.require_cuda()
+        print(f'Movement model = {self.movement_model}')
+        print(f'Updraft threshold = {self.updraft_threshold} m/s')
+        print(f'Movement direction = {self.track_direction} deg (cw)')
+        starting_rows, starting_cols = get_starting_indices(
+            self.track_count, self.track_start_region, self.track_start_type, self.region_width_km, self.resolution)
+        n = len(starting_rows)
+        lo, hi = _dist.shard_range(n, _dist.rank(), _dist.world_size())
+        record = (n <= TRACKS_PKL_LIMIT) if save_tracks is None else bool(save_tracks)
+        for ci, case_id in enumerate(self.case_ids):
+            updraft = self._load_updraft_device(case_id)
+            for real_id in range(1):
+                if self.sim_seed > 0:
+                    np.random.seed(self.sim_seed + real_id)              # reference :351-352
+                id_str = self._get_id_string(case_id, real_id)
+                fields = None
+                if self.movement_model == 'fluidflow':
+                    self.get_directional_potential(updraft, case_id, real_id)
+                    fields = interleave_fields(updraft, self._last_potential_device)
+                elif self.movement_model != 'drw':
+                    raise ValueError(f'Invalid movement_model {self.movement_model!r}; options: fluidflow, drw')
+                print(f'{id_str}: Simulating {self.track_count} tracks..', end="", flush=True)
+                t0 = time.time()
+                res = simulate_tracks_batch(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
+                                            self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
+                                            fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
+                                            record=record)
+                presence = _dist.allreduce_sum(res.presence)
+                steps = _dist.allreduce_sum(res._total.clone())
+                torch.cuda.synchronize()
+                self.timings['tracks_s'] = time.time() - t0
+                self.total_track_steps = int(steps.item())
+                print(f'took {_elapsed(t0)}', flush=True)
+                self._presence[id_str] = presence
+                fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
+                if record:
+                    tracks = res.tracks()
+                    tracks = _dist.gather_tracks(tracks)
+                    if _dist.rank() == 0:
+                        with open(f'{fname}.pkl', 'wb') as fobj:
+                            pickle.dump(tracks, fobj)
+                elif _dist.rank() == 0:
+                    np.savez_compressed(f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
+
+    def presence_counts(self, case_id: Optional[str] = None, real_id: int = 0) -> np.ndarray:
+        """int32 visit counts of the last simulate_tracks() (reference compute_presence_counts, movmodel.py:410-419)."""
+        case_id = self.case_ids[0] if case_id is None else case_id
+        return self._presence[self._get_id_string(case_id, real_id)].cpu().numpy()
+
+    def _get_tracks_fname(self, case_id: str, real_id: int, dirname: str):
+        return os.path.join(dirname, f'{self._get_id_string(case_id, real_id)}_tracks')
+
+    def _get_presence_fname(self, case_id: str, real_id: int, dirname: str):
+        return os.path.join(dirname, f'{self._get_id_string(case_id, real_id)}_presence')
+
+    def compute_presence_map(self, radius: float = 1000.) -> np.ndarray:
+        """Data part of the reference's plot_presence_map (:508-546): smooth each realisation's counts with the
+        disk kernel, normalise by the maxima, sum over cases, save `summary_presence.npy` (float32)."""
+        from .presence import smooth_presence_counts
+        krad = min(max(radius / self.resolution, 2), min(self.gridsize) / 2)
+        summary = None
+        for case_id in self.case_ids:
+            case_prob = None
+            for real_id in range(1):
+                counts = self._presence[self._get_id_string(case_id, real_id)]
+                pr = smooth_presence_counts(counts, int(round(krad)))
+                pr = pr / pr.max()
+                case_prob = pr if case_prob is None else case_prob + pr
+            case_prob = case_prob / case_prob.max()
+            summary = case_prob if summary is None else summary + case_prob
+        summary = (summary / summary.max()).float().cpu().numpy()
+        if _dist.rank() == 0:
+            np.save(os.path.join(self.mode_data_dir, 'summary_presence.npy'), summary)
+        return summary
+
+    def plot_presence_map(self, plot_turbs=True, radius: float = 1000., show=False, minval=0.1, plot_all: bool = False):
+        """Computes and saves the summary presence raster; figures are outside the hot path (no matplotlib)."""
+        print('Computing presence density map (figures are not produced by ssrs_b200)..')
+        return self.compute_presence_map(radius)
+
+    def _no_plots(self, *a, **k):
+        raise NotImplementedError("plotting is outside the B200 hot path (SURVEY.md §2 row 5); the data products "
+                                  "(.npy/.pkl) are written with the reference's names, so the reference's plot_* "
+                                  "methods can read them")
+
+    plot_directional_potentials = plot_simulated_tracks = plot_updrafts = plot_wtk_layers = _no_plots
+    plot_terrain_features = plot_terrain_elevation = plot_terrain_slope = plot_terrain_aspect = _no_plots
+    plot_windplant_presence_map = plot_updraft_threshold_function = _no_plots
+
+    def _get_uniform_id(self):
+        return f's{int(self.uniform_windspeed)}d{int(self.uniform_winddirn)}'
