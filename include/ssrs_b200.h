@@ -115,19 +115,24 @@ SSRS_API int ssrs_potential_solve(const float* conductivity, int rows, int cols,
  *         uniforms[t*uniforms_stride + k] — the reference's pre-drawn np.random stream; otherwise
  *         Philox4x32-10 keyed by seed with counter (track_id0 + t, k), so results do not depend on
  *         how tracks are sharded over GPUs.
+ * flags: 0, or SSRS_STEP_EXACT to evaluate the probabilities in the reference's exact operation order
+ *         (bit-for-bit numpy; always used in verification mode).  The default production arithmetic cancels
+ *         the normalisations (same distribution, ~7x fewer float64 operations).
  * traj (optional): int16 [traj_cap][n_tracks][2] step-major (row, col); points beyond traj_cap are
  *         not stored but still stepped and counted.   traj_len (optional): int32 [n_tracks] number of
  *         trajectory points (= steps + 1).   presence (optional): uint32 [rows][cols], incremented
  *         atomically (not cleared).   total_steps (optional): one uint64, incremented by the number
  *         of track-steps taken (loop iterations at ssrs/movmodel.py:285-317).
  */
+#define SSRS_STEP_EXACT 1
+
 SSRS_API int ssrs_step_tracks(const float* fields, int rows, int cols,
                      const int32_t* start_rc, int64_t n_tracks, int64_t track_id0,
                      const double* dirprob9_host, int memory, double nu,
                      uint64_t seed, const double* uniforms, int64_t uniforms_stride,
                      int16_t* traj, int64_t traj_cap, int32_t* traj_len,
                      uint32_t* presence, unsigned long long* total_steps,
-                     void* stream);
+                     int flags, void* stream);
 
 /* {updraft, potential} -> interleaved pairs (one 8-byte gather per cell in the stepping kernel). */
 SSRS_API int ssrs_interleave_fields(const float* updraft, const float* potential, float* fields,

@@ -22,7 +22,7 @@ def lib():
         _lib.oracle_step_tracks.restype = C.c_int64
         _lib.oracle_step_tracks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_void_p, C.c_int64,
-                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _lib.oracle_presence_counts.restype = None
         _lib.oracle_presence_counts.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         _lib.oracle_philox_uniform.restype = C.c_double
@@ -35,9 +35,10 @@ def _ptr(a):
 
 
 def step_tracks(U, P, shape, start_rc, move_dirn, memory=1, nu=1.0, seed=0, track_id0=0, uniforms=None,
-                traj_cap=0, want_presence=True, nthreads=1):
+                traj_cap=0, want_presence=True, nthreads=1, fast=False):
     """Runs the C oracle.  U, P: float32 [rows, cols] or both None ('drw').  start_rc int32 [n,2].
-    uniforms: float64 [n, stride] (verification) or None (Philox).  Returns dict(total_steps, traj_len,
+    uniforms: float64 [n, stride] (verification) or None (Philox).  fast=False: the reference's exact operation
+    order; fast=True: the CUDA stepper's production arithmetic (same distribution, fewer divisions).  Returns dict(total_steps, traj_len,
     traj [n,cap,2] or None, presence int32 or None)."""
     rows, cols = shape
     start_rc = np.ascontiguousarray(start_rc, dtype=np.int32)
@@ -56,7 +57,7 @@ def step_tracks(U, P, shape, start_rc, move_dirn, memory=1, nu=1.0, seed=0, trac
     presence = np.zeros((rows, cols), dtype=np.int32) if want_presence else None
     total = lib().oracle_step_tracks(_ptr(U), _ptr(P), rows, cols, _ptr(start_rc), n, track_id0, _ptr(dirp),
                                      int(memory), float(nu), int(seed), _ptr(uniforms), ustride, _ptr(traj),
-                                     traj_cap, _ptr(traj_len), _ptr(presence), int(nthreads))
+                                     traj_cap, _ptr(traj_len), _ptr(presence), int(nthreads), int(bool(fast)))
     return dict(total_steps=int(total), traj_len=traj_len, traj=traj, presence=presence)
 
 

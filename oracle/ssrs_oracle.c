@@ -44,16 +44,119 @@ static double pairwise9(const double* p) {
     return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
 }
 
+/* Move selection in the reference's exact operation order (movmodel.py:294-312). */
+static int choose_exact(const float* U, const float* P, int nc, int r, int c, const double* dirp, unsigned mask,
+                        double nu, double u) {
+    const float ninv_d = 0.70710677f;
+    double p[9];
+    int any_nan = 0;
+    if (U != NULL) {
+        const int64_t o = (int64_t)r * nc + c;
+        double uc = (double)U[o]; if (uc < 1e-06) uc = 1e-06;      /* :295 */
+        const double iuc = 1.0 / uc;
+        for (int i = 0; i < 9; ++i) {
+            const int dr = i / 3 - 1, dc = i % 3 - 1;
+            const int64_t q = o + (int64_t)dr * nc + dc;
+            double ui = (double)U[q]; if (ui < 1e-06) ui = 1e-06;
+            const double w = 2.0 / (iuc + 1.0 / ui);               /* :296, :260-261 */
+            const float ninv = (i == 4) ? 0.0f : ((dr != 0 && dc != 0) ? ninv_d : 1.0f);
+            const float d = (float)(P[o] - P[q]) * ninv;           /* float32, :301-304 */
+            p[i] = w * (double)d;                                  /* :305 */
+            if (p[i] != p[i]) any_nan = 1;
+        }
+    } else {
+        for (int i = 0; i < 9; ++i) p[i] = dirp[i];                /* :298-299 */
+    }
+    if (any_nan) for (int i = 0; i < 9; ++i) p[i] = dirp[i];       /* :228-230 */
+    int nz = 0;
+    for (int i = 0; i < 9; ++i) {                                  /* :231-233 */
+        if (p[i] < 0.0) p[i] = 0.0;
+        if (i == 4 || !((mask >> i) & 1u)) p[i] = 0.0;
+        if (p[i] != 0.0) nz++;
+    }
+    if (nz == 0) {                                                 /* :234-238 */
+        for (int i = 0; i < 9; ++i) {
+            p[i] = (i == 4 || !((mask >> i) & 1u)) ? 0.0 : dirp[i];
+            if (p[i] != 0.0) nz++;
+        }
+    }
+    if (nz == 0) for (int i = 0; i < 9; ++i) p[i] = dirp[i];       /* :239-240 */
+    double s = pairwise9(p);                                       /* :241 */
+    for (int i = 0; i < 9; ++i) p[i] = p[i] / s;
+    if (nu != 1.0) for (int i = 0; i < 9; ++i) p[i] = pow(p[i], nu);   /* :242 */
+    s = pairwise9(p);                                              /* :243 */
+    for (int i = 0; i < 9; ++i) p[i] = p[i] / s;
+    double cdf[9];
+    cdf[0] = p[0];
+    for (int i = 1; i < 9; ++i) cdf[i] = cdf[i - 1] + p[i];
+    const double tot = cdf[8];
+    int idx = 0;
+    for (int i = 0; i < 9; ++i) if (cdf[i] / tot <= u) idx++;      /* searchsorted side='right' */
+    if (idx > 8) idx = 8;
+    return idx;
+}
+
+/* "Production arithmetic" of the CUDA stepper (ssrs_b200/csrc/tracks.cu, choose_fast): the normalisations of
+ * movmodel.py:241-243 and of np.random.choice cancel, so q_i = max(d_i,0) * u_i / (u_c + u_i) (= p_i / (2 u_c))
+ * and the move is the first index whose running sum exceeds u * sum(q).  Same distribution as choose_exact up to
+ * rounding of the cdf boundaries; restated here operation for operation so GPU production runs can be checked
+ * bit for bit on the CPU.  Only mask-allowed neighbours are evaluated (also for the NaN test). */
+static int choose_fast(const float* U, const float* P, int nc, int r, int c, const double* dirp, unsigned mask,
+                       double nu, double u) {
+    const float ninv_d = 0.70710677f;
+    double q[9];
+    int any_nan = 0, nz = 0;
+    const int64_t o = (int64_t)r * nc + c;
+    double uc = 0.0;
+    if (U != NULL) { uc = (double)U[o]; if (uc < 1e-06) uc = 1e-06; }
+    for (int i = 0; i < 9; ++i) {
+        q[i] = 0.0;
+        if (i == 4 || !((mask >> i) & 1u)) continue;
+        if (U == NULL) { q[i] = dirp[i]; }
+        else {
+            const int dr = i / 3 - 1, dc = i % 3 - 1;
+            const int64_t qn = o + (int64_t)dr * nc + dc;
+            const float ninv = (dr != 0 && dc != 0) ? ninv_d : 1.0f;
+            const float d = (float)(P[o] - P[qn]) * ninv;
+            if (d != d) any_nan = 1;
+            if (d > 0.0f) {
+                double ui = (double)U[qn]; if (ui < 1e-06) ui = 1e-06;
+                q[i] = ((double)d * ui) / (uc + ui);
+            }
+        }
+        if (q[i] != 0.0) nz++;
+    }
+    if (any_nan || nz == 0) {
+        nz = 0;
+        for (int i = 0; i < 9; ++i) {
+            q[i] = (i == 4 || !((mask >> i) & 1u)) ? 0.0 : dirp[i];
+            if (q[i] != 0.0) nz++;
+        }
+        if (nz == 0) for (int i = 0; i < 9; ++i) q[i] = dirp[i];
+    }
+    if (nu != 1.0) for (int i = 0; i < 9; ++i) q[i] = pow(q[i], nu);
+    double tot = 0.0;
+    for (int i = 0; i < 9; ++i) tot += q[i];
+    const double target = u * tot;
+    double run = 0.0;
+    int idx = -1, last_pos = 4;
+    for (int i = 0; i < 9; ++i) {
+        run += q[i];
+        if (q[i] > 0.0) last_pos = i;
+        if (idx < 0 && run > target) idx = i;
+    }
+    return idx >= 0 ? idx : last_pos;
+}
+
 /* One track.  U (float32, widened to double as the reference's float64 updraft) and P (float32) are
  * [rows][cols]; either both given (fluid-flow) or both NULL ('drw').  uniforms: per-step numbers for this
  * track or NULL for Philox(seed, gid, k).  traj: optional int16 [cap][2].  presence: optional int32
  * [rows][cols] (incremented; atomically when built with OpenMP).  Returns the number of points. */
 static int64_t one_track(const float* U, const float* P, int nr, int nc, int row, int col, const double* dirp,
                          int memory, double nu, uint64_t seed, uint64_t gid, const double* uniforms,
-                         int16_t* traj, int64_t cap, int32_t* presence) {
+                         int16_t* traj, int64_t cap, int32_t* presence, int fast) {
     const int burnin = (int)((nr < nc ? nr : nc) / 10);                /* :276 */
     const double max_moves = (double)nr / 2 * (double)nc / 2;          /* :277 */
-    const float ninv_d = 0.70710677f;
     int hist_len = 1, hist_cap = 64;
     unsigned char* hist = (unsigned char*)malloc((size_t)hist_cap);    /* directions list, :280-281 */
     hist[0] = 4;
@@ -76,52 +179,10 @@ static int64_t one_track(const float* U, const float* P, int nr, int nc, int row
             int m = (memory == 0 || memory > hist_len) ? hist_len : memory;   /* directions[-0:] is the whole list */
             for (int j = 0; j < m; ++j) mask &= RESTRICT_LUT[hist[hist_len - 1 - j]];
         }
-        double p[9];
-        int any_nan = 0;
-        if (U != NULL) {
-            const int64_t o = (int64_t)r * nc + c;
-            double uc = (double)U[o]; if (uc < 1e-06) uc = 1e-06;      /* :295 */
-            const double iuc = 1.0 / uc;
-            for (int i = 0; i < 9; ++i) {
-                const int dr = i / 3 - 1, dc = i % 3 - 1;
-                const int64_t q = o + (int64_t)dr * nc + dc;
-                double ui = (double)U[q]; if (ui < 1e-06) ui = 1e-06;
-                const double w = 2.0 / (iuc + 1.0 / ui);               /* :296, :260-261 */
-                const float ninv = (i == 4) ? 0.0f : ((dr != 0 && dc != 0) ? ninv_d : 1.0f);
-                const float d = (float)(P[o] - P[q]) * ninv;           /* float32, :301-304 */
-                p[i] = w * (double)d;                                  /* :305 */
-                if (p[i] != p[i]) any_nan = 1;
-            }
-        } else {
-            for (int i = 0; i < 9; ++i) p[i] = dirp[i];                /* :298-299 */
-        }
-        if (any_nan) for (int i = 0; i < 9; ++i) p[i] = dirp[i];       /* :228-230 */
-        int nz = 0;
-        for (int i = 0; i < 9; ++i) {                                  /* :231-233 */
-            if (p[i] < 0.0) p[i] = 0.0;
-            if (i == 4 || !((mask >> i) & 1u)) p[i] = 0.0;
-            if (p[i] != 0.0) nz++;
-        }
-        if (nz == 0) {                                                 /* :234-238 */
-            for (int i = 0; i < 9; ++i) {
-                p[i] = (i == 4 || !((mask >> i) & 1u)) ? 0.0 : dirp[i];
-                if (p[i] != 0.0) nz++;
-            }
-        }
-        if (nz == 0) for (int i = 0; i < 9; ++i) p[i] = dirp[i];       /* :239-240 */
-        double s = pairwise9(p);                                       /* :241 */
-        for (int i = 0; i < 9; ++i) p[i] = p[i] / s;
-        if (nu != 1.0) for (int i = 0; i < 9; ++i) p[i] = pow(p[i], nu);   /* :242 */
-        s = pairwise9(p);                                              /* :243 */
-        for (int i = 0; i < 9; ++i) p[i] = p[i] / s;
         const double u = uniforms ? uniforms[k] : oracle_philox_uniform(seed, gid, (uint32_t)k);
-        double cdf[9];
-        cdf[0] = p[0];
-        for (int i = 1; i < 9; ++i) cdf[i] = cdf[i - 1] + p[i];
-        const double tot = cdf[8];
-        int idx = 0;
-        for (int i = 0; i < 9; ++i) if (cdf[i] / tot <= u) idx++;      /* searchsorted side='right' */
-        if (idx > 8) idx = 8;
+        int idx;
+        if (fast) idx = choose_fast(U, P, nc, r, c, dirp, mask, nu, u);
+        else idx = choose_exact(U, P, nc, r, c, dirp, mask, nu, u);
         row = r + (idx / 3 - 1);                                       /* :313-317 */
         col = c + (idx % 3 - 1);
         ++k;
@@ -142,7 +203,7 @@ static int64_t one_track(const float* U, const float* P, int nr, int nc, int row
 int64_t oracle_step_tracks(const float* U, const float* P, int rows, int cols, const int32_t* start_rc, int64_t n,
                            int64_t track_id0, const double* dirp, int memory, double nu, uint64_t seed,
                            const double* uniforms, int64_t ustride, int16_t* traj, int64_t cap, int32_t* traj_len,
-                           int32_t* presence, int nthreads) {
+                           int32_t* presence, int nthreads, int fast) {
     int64_t total = 0;
 #ifdef _OPENMP
     if (nthreads < 1) nthreads = 1;
@@ -151,7 +212,7 @@ int64_t oracle_step_tracks(const float* U, const float* P, int rows, int cols, c
     for (int64_t t = 0; t < n; ++t) {
         int64_t len = one_track(U, P, rows, cols, start_rc[2 * t], start_rc[2 * t + 1], dirp, memory, nu, seed,
                                 (uint64_t)(track_id0 + t), uniforms ? uniforms + t * ustride : NULL,
-                                traj ? traj + t * cap * 2 : NULL, cap, presence);
+                                traj ? traj + t * cap * 2 : NULL, cap, presence, fast);
         if (traj_len) traj_len[t] = (int32_t)len;
         total += len - 1;
     }

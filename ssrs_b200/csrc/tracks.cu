@@ -73,12 +73,166 @@ __device__ __forceinline__ double pairwise9(const double* p) {
     return (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
 }
 
+// ---- move selection, exact arithmetic ---------------------------------------------------------------
+// Reproduces numpy bit for bit (movmodel.py:294-312): used in verification mode and on request.
 template <bool HAS_FIELDS>
-__global__ void __launch_bounds__(128, 4) step_tracks_kernel(const TrackParams P) {
+__device__ __forceinline__ int choose_exact(const TrackParams& P, const float2* base, int nc, unsigned mask, double u) {
+    const float NINV_D = 0.70710677f;     // float32(1/sqrt(2)), movmodel.py:139-141
+    double p[9];
+    bool any_nz = false, any_nan = false;
+    if (HAS_FIELDS) {
+        const float2 fc = __ldg(base);
+        const double uc = fmax((double)fc.x, 1e-06);                    // :295
+        const double iuc = 1.0 / uc;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            p[i] = 0.0;
+            if (i != 4 && ((mask >> i) & 1u)) {
+                const int dr = i / 3 - 1, dc = i % 3 - 1;
+                const float2 f = __ldg(base + dr * nc + dc);
+                const double ui = fmax((double)f.x, 1e-06);
+                const double w = 2.0 / (iuc + 1.0 / ui);                // :296, :260-261
+                const float ninv = (dr != 0 && dc != 0) ? NINV_D : 1.0f;
+                const float d = __fmul_rn(__fsub_rn(fc.y, f.y), ninv);  // float32, :301-304
+                double v = w * (double)d;                               // :305
+                any_nan |= (v != v);
+                v = v > 0.0 ? v : 0.0;                                  // clip(min=0), :231
+                p[i] = v;
+                any_nz |= (v != 0.0);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {                                    // 'drw': p = directional, :298-299
+            p[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0;
+            any_nz |= (p[i] != 0.0);
+        }
+    }
+    if (any_nan || !any_nz) {                                           // :228-230, :234-236
+        any_nz = false;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            p[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0;
+            any_nz |= (p[i] != 0.0);
+        }
+        if (!any_nz) {                                                  // :239-240 (mask ignored)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) p[i] = P.dirp[i];
+        }
+    }
+    double s = pairwise9(p);                                            // :241
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p[i] = (p[i] != 0.0) ? p[i] / s : 0.0;
+    if (!P.nu_is_one) {                                                 // :242
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p[i] = pow(p[i], P.nu);
+    }
+    s = pairwise9(p);                                                   // :243
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p[i] = (p[i] != 0.0) ? p[i] / s : 0.0;
+    // np.random.choice (:312): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, side='right')
+    double cdf[9];
+    cdf[0] = p[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) cdf[i] = cdf[i - 1] + p[i];
+    const double tot = cdf[8];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) idx += ((cdf[i] / tot) <= u) ? 1 : 0;
+    return idx > 8 ? 8 : idx;
+}
+
+// ---- move selection, production arithmetic --------------------------------------------------------------
+// Same distribution with the normalisations cancelled: only ratios of the weights matter, so
+//   q_i = max(d_i, 0) * u_i / (u_c + u_i)      (= p_i / (2 u_c), movmodel.py:296-305)
+// and the move is the first i (ascending flat index) whose running sum exceeds u * sum(q).  The two
+// normalising divisions, the cdf division and 2/(1/a+1/b) of the exact form are gone: at most one division
+// per allowed neighbour.  A draw differs from the exact form only if u lies within rounding (~1e-16) of a
+// cdf boundary.  oracle/ssrs_oracle.c implements the same arithmetic (mode "fast"), so production runs are
+// still reproduced bit for bit on the CPU.
+template <bool HAS_FIELDS>
+__device__ __forceinline__ double weight_fast(const TrackParams& P, const float2* base, const float2 fc, double uc,
+                                              int nc, int i, bool& any_nan) {
+    if (!HAS_FIELDS) return P.dirp[i];
+    const int dr = i / 3 - 1, dc = i % 3 - 1;
+    const float2 f = __ldg(base + dr * nc + dc);
+    const float ninv = (dr != 0 && dc != 0) ? 0.70710677f : 1.0f;
+    const float d = __fmul_rn(__fsub_rn(fc.y, f.y), ninv);               // float32, :301-304
+    any_nan |= (d != d);
+    if (!(d > 0.0f)) return 0.0;
+    const double ui = fmax((double)f.x, 1e-06);
+    return ((double)d * ui) / (uc + ui);
+}
+
+// all nine entries (first step of a track, nu != 1, or the unmasked directional fallback)
+template <bool HAS_FIELDS>
+__device__ __noinline__ int choose_fast_general(const TrackParams& P, const float2* base, int nc, unsigned mask, double u) {
+    double q[9];
+    bool any_nz = false, any_nan = false;
+    float2 fc = make_float2(0.f, 0.f);
+    double uc = 0.0;
+    if (HAS_FIELDS) { fc = __ldg(base); uc = fmax((double)fc.x, 1e-06); }
+    for (int i = 0; i < 9; ++i) {
+        q[i] = (i != 4 && ((mask >> i) & 1u)) ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i, any_nan) : 0.0;
+        any_nz |= (q[i] != 0.0);
+    }
+    if (any_nan || !any_nz) {
+        any_nz = false;
+        for (int i = 0; i < 9; ++i) { q[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0; any_nz |= (q[i] != 0.0); }
+        if (!any_nz)
+            for (int i = 0; i < 9; ++i) q[i] = P.dirp[i];
+    }
+    if (!P.nu_is_one)
+        for (int i = 0; i < 9; ++i) q[i] = pow(q[i], P.nu);
+    double run = 0.0, tot = 0.0;
+    for (int i = 0; i < 9; ++i) tot += q[i];
+    const double target = u * tot;
+    int idx = -1, last_pos = 4;
+    for (int i = 0; i < 9; ++i) {
+        run += q[i];
+        if (q[i] > 0.0) last_pos = i;
+        if (idx < 0 && run > target) idx = i;
+    }
+    return idx >= 0 ? idx : last_pos;
+}
+
+// the three neighbours within 45 degrees of the previous move, ascending flat index, 4 bits each
+constexpr unsigned long long C3_A = (0x310ULL) | (0x210ULL << 12) | (0x521ULL << 24) | (0x630ULL << 36) | (0x000ULL << 48);
+constexpr unsigned long long C3_B = (0x852ULL) | (0x763ULL << 12) | (0x876ULL << 24) | (0x875ULL << 36);
+
+template <bool HAS_FIELDS>
+__device__ __forceinline__ int choose_fast(const TrackParams& P, const float2* base, int nc, unsigned mask,
+                                           unsigned last, double u) {
+    if (last == 4u || !P.nu_is_one) return choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
+    const unsigned c3 = (unsigned)((last < 5 ? (C3_A >> (12 * last)) : (C3_B >> (12 * (last - 5)))) & 0xFFFu);
+    const int i0 = c3 & 15, i1 = (c3 >> 4) & 15, i2 = (c3 >> 8) & 15;
+    const bool e0 = (mask >> i0) & 1u, e1 = (mask >> i1) & 1u, e2 = (mask >> i2) & 1u;
+    bool any_nan = false;
+    float2 fc = make_float2(0.f, 0.f);
+    double uc = 0.0;
+    if (HAS_FIELDS) { fc = __ldg(base); uc = fmax((double)fc.x, 1e-06); }
+    double q0 = e0 ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i0, any_nan) : 0.0;
+    double q1 = e1 ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i1, any_nan) : 0.0;
+    double q2 = e2 ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i2, any_nan) : 0.0;
+    if (any_nan || (q0 == 0.0 && q1 == 0.0 && q2 == 0.0)) {
+        q0 = e0 ? P.dirp[i0] : 0.0;
+        q1 = e1 ? P.dirp[i1] : 0.0;
+        q2 = e2 ? P.dirp[i2] : 0.0;
+        if (q0 == 0.0 && q1 == 0.0 && q2 == 0.0) return choose_fast_general<false>(P, base, nc, 0u, u);  // unmasked directional
+    }
+    const double c0 = q0, c1 = c0 + q1, c2 = c1 + q2;
+    const double target = u * c2;
+    if (c0 > target) return i0;
+    if (c1 > target) return i1;
+    if (c2 > target) return i2;
+    return q2 > 0.0 ? i2 : (q1 > 0.0 ? i1 : i0);
+}
+
+template <bool HAS_FIELDS, bool EXACT>
+__global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nr = P.rows, nc = P.cols;
-    const float NINV_D = 0.70710677f;     // float32(1/sqrt(2)), movmodel.py:139-141
     unsigned long long steps_local = 0;
     bool alive = false;
     int row = 0, col = 0, k = 0;
@@ -113,68 +267,16 @@ __global__ void __launch_bounds__(128, 4) step_tracks_kernel(const TrackParams P
             continue;
         }
         // direction-memory mask (:307-309)
+        const unsigned last = (unsigned)(hist & 15);
         unsigned mask;
-        if (P.memory == 1) mask = restrict_mask((unsigned)(hist & 15));
+        if (P.memory == 1) mask = restrict_mask(last);
         else if (P.memory == 0) mask = run_mask;
         else {
             mask = 0x1EF;
             int m = P.memory < hcount ? P.memory : hcount;
             for (int j = 0; j < m; ++j) mask &= restrict_mask((unsigned)((hist >> (4 * j)) & 15));
         }
-        double p[9];
-        bool any_nz = false, any_nan = false;
-        if (HAS_FIELDS) {
-            const float2* base = P.fields + (long long)r * nc + c;
-            const float2 fc = __ldg(base);
-            const double uc = fmax((double)fc.x, 1e-06);                    // :295
-            const double iuc = 1.0 / uc;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                p[i] = 0.0;
-                if (i != 4 && ((mask >> i) & 1u)) {
-                    const int dr = i / 3 - 1, dc = i % 3 - 1;
-                    const float2 f = __ldg(base + dr * nc + dc);
-                    const double ui = fmax((double)f.x, 1e-06);
-                    const double w = 2.0 / (iuc + 1.0 / ui);                // :296, :260-261
-                    const float ninv = (dr != 0 && dc != 0) ? NINV_D : 1.0f;
-                    const float d = __fmul_rn(__fsub_rn(fc.y, f.y), ninv);  // float32, :301-304
-                    double v = w * (double)d;                               // :305
-                    any_nan |= (v != v);
-                    v = v > 0.0 ? v : 0.0;                                  // clip(min=0), :231
-                    p[i] = v;
-                    any_nz |= (v != 0.0);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {                                    // 'drw': p = directional, :298-299
-                p[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0;
-                any_nz |= (p[i] != 0.0);
-            }
-        }
-        if (any_nan || !any_nz) {                                           // :228-230, :234-236
-            any_nz = false;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                p[i] = (i != 4 && ((mask >> i) & 1u)) ? P.dirp[i] : 0.0;
-                any_nz |= (p[i] != 0.0);
-            }
-            if (!any_nz) {                                                  // :239-240 (mask ignored)
-#pragma unroll
-                for (int i = 0; i < 9; ++i) p[i] = P.dirp[i];
-            }
-        }
-        double s = pairwise9(p);                                            // :241
-#pragma unroll
-        for (int i = 0; i < 9; ++i) p[i] = (p[i] != 0.0) ? p[i] / s : 0.0;
-        if (!P.nu_is_one) {                                                 // :242
-#pragma unroll
-            for (int i = 0; i < 9; ++i) p[i] = pow(p[i], P.nu);
-        }
-        s = pairwise9(p);                                                   // :243
-#pragma unroll
-        for (int i = 0; i < 9; ++i) p[i] = (p[i] != 0.0) ? p[i] / s : 0.0;
-        // np.random.choice (:312): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, side='right')
+        // one uniform per step (:312)
         double u;
         if (P.uniforms != nullptr) {
             u = __ldg(P.uniforms + t * P.ustride + k);
@@ -185,15 +287,9 @@ __global__ void __launch_bounds__(128, 4) step_tracks_kernel(const TrackParams P
                           (unsigned)(P.seed >> 32), a, b);
             u = uniform53(a, b);
         }
-        double cdf[9];
-        cdf[0] = p[0];
-#pragma unroll
-        for (int i = 1; i < 9; ++i) cdf[i] = cdf[i - 1] + p[i];
-        const double tot = cdf[8];
-        int idx = 0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) idx += ((cdf[i] / tot) <= u) ? 1 : 0;
-        idx = idx > 8 ? 8 : idx;
+        const float2* base = HAS_FIELDS ? P.fields + (long long)r * nc + c : nullptr;
+        const int idx = EXACT ? choose_exact<HAS_FIELDS>(P, base, nc, mask, u)
+                              : choose_fast<HAS_FIELDS>(P, base, nc, mask, last, u);
         row = r + (idx / 3 - 1);                                            // :313-317
         col = c + (idx % 3 - 1);
         ++k;
@@ -243,7 +339,7 @@ extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const i
                                 int64_t track_id0, const double* dirprob9_host, int memory, double nu, uint64_t seed,
                                 const double* uniforms, int64_t uniforms_stride, int16_t* traj, int64_t traj_cap,
                                 int32_t* traj_len, uint32_t* presence, unsigned long long* total_steps,
-                                void* stream) {
+                                int flags, void* stream) {
     SSRS_REQUIRE(rows >= 5 && cols >= 5, "ssrs_step_tracks: grid %dx%d too small", rows, cols);
     SSRS_REQUIRE(rows <= 32767 && cols <= 32767, "ssrs_step_tracks: int16 trajectories need rows, cols <= 32767");
     SSRS_REQUIRE(n_tracks >= 0 && track_id0 >= 0, "ssrs_step_tracks: negative track count or id");
@@ -272,13 +368,21 @@ extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const i
     P.rows = rows; P.cols = cols;
     P.burnin = (int)((rows < cols ? rows : cols) / 10);                      // movmodel.py:276
     P.memory = memory;
+    // verification mode always uses the exact (numpy bit-for-bit) arithmetic
+    const bool exact = (uniforms != nullptr) || (flags & SSRS_STEP_EXACT);
     const int threads = 128;
+    void (*kern)(const TrackParams) =
+        fields != nullptr ? (exact ? step_tracks_kernel<true, true> : step_tracks_kernel<true, false>)
+                          : (exact ? step_tracks_kernel<false, true> : step_tracks_kernel<false, false>);
+    // as many tracks resident at once as the registers allow: the kernel is latency-bound and its duration is
+    // set by the longest track, so every track should start at time zero
+    int per_sm = 0;
+    SSRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    if (per_sm < 1) per_sm = 1;
     long long blocks = cdiv(n_tracks, threads);
-    const long long cap = (long long)sm_count() * 4;
+    const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (fields != nullptr) step_tracks_kernel<true><<<(int)blocks, threads, 0, st>>>(P);
-    else step_tracks_kernel<false><<<(int)blocks, threads, 0, st>>>(P);
+    kern<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(P);
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
 }

@@ -59,25 +59,51 @@ __device__ __forceinline__ float threshold_fn(float w, float thr, float thr_inv,
     return thr * expm1f(t2 * t2 * t) * inv_em1;
 }
 
+// atan(t) for t in [0, 1]: t * P(t^2), degree-6 minimax fit (max error 3.2e-7 rad = 1.8e-5 degrees,
+// i.e. ~1e-6 of the slope range and ~5e-8 of the aspect range; the contract is 1e-5 of each field's maximum).
+__device__ __forceinline__ float atan01(float t) {
+    const float s = t * t;
+    float p = 0.006811788771301508f;
+    p = fmaf(p, s, -0.0336042158305645f);
+    p = fmaf(p, s, 0.07962367683649063f);
+    p = fmaf(p, s, -0.132333442568779f);
+    p = fmaf(p, s, 0.19807817041873932f);
+    p = fmaf(p, s, -0.3331736922264099f);
+    p = fmaf(p, s, 0.9999961256980896f);
+    return p * t;
+}
+
 // One cell.  Arguments are the nine DEM samples named as in layers.py:80-88 would index them:
 // n* = row r+1, m* = row r, s* = row r-1 ; *w = col c-1, *c = col c, *e = col c+1.
+// Square roots and quotients go through MUFU.RSQ / MUFU.RCP (<= 2 ulp), inverse tangents through atan01.
+template <bool WANT_ANGLES>
 __device__ __forceinline__ void cell(float sw_, float sc_, float se_, float mw_, float me_,
                                      float nw_, float nc_, float ne_,
                                      float inv8res, float V, float sinw, float cosw,
                                      float& slope, float& aspect, float& oro) {
     // dz_dx: derivative along axis 0 (rows) ; dz_dy: along axis 1 (cols)   (layers.py:89-90)
-    float gx = ((ne_ - se_) + 2.0f * (nc_ - sc_) + (nw_ - sw_)) * inv8res;
-    float gy = ((se_ - sw_) + 2.0f * (me_ - mw_) + (ne_ - nw_)) * inv8res;
-    float h2 = gx * gx + gy * gy;
-    float h = sqrtf(h2);
-    slope = atanf(h) * 57.29577951308232f;
-    float gxa = (gx == 0.0f) ? 1e-10f : gx;                               // layers.py:124
-    float ang = atanf(gy / gxa) * 57.29577951308232f;
-    aspect = 180.0f - ang + copysignf(90.0f, gxa);                       // layers.py:125-127
-    float ha = sqrtf(gxa * gxa + gy * gy);
-    float cosd = -(gy * cosw + gxa * sinw) / ha;
-    float sins = h * rsqrtf(1.0f + h2);
+    const float gx = ((ne_ - se_) + 2.0f * (nc_ - sc_) + (nw_ - sw_)) * inv8res;
+    const float gy = ((se_ - sw_) + 2.0f * (me_ - mw_) + (ne_ - nw_)) * inv8res;
+    const float h2 = fmaf(gx, gx, gy * gy);
+    const float h = h2 > 0.0f ? h2 * rsqrtf(h2) : 0.0f;
+    const float gxa = (gx == 0.0f) ? 1e-10f : gx;                         // layers.py:124
+    const float rha = rsqrtf(fmaf(gxa, gxa, gy * gy));
+    const float cosd = -(gy * cosw + gxa * sinw) * rha;                   // cos(aspect - wdir)
+    const float sins = h * rsqrtf(1.0f + h2);                             // sin(atan(h))
     oro = fmaxf(0.0f, V * sins * fmaxf(0.0f, cosd));                      // layers.py:19-22
+    if (WANT_ANGLES) {
+        const bool steep = h > 1.0f;
+        float a = atan01(steep ? __fdividef(1.0f, h) : h);
+        slope = (steep ? 1.5707963267948966f - a : a) * 57.29577951308232f;
+        const float ay = fabsf(gy), ax = fabsf(gxa);
+        float p = atan01(__fdividef(fminf(ay, ax), fmaxf(ay, ax)));
+        p = ay > ax ? 1.5707963267948966f - p : p;
+        const float ang = ((gy < 0.0f) != (gxa < 0.0f)) ? -p : p;         // atan(dz_dy / dz_dx)
+        aspect = 180.0f - ang * 57.29577951308232f + copysignf(90.0f, gxa);   // layers.py:125-127
+    } else {
+        slope = 0.0f;
+        aspect = 0.0f;
+    }
 }
 
 struct Row6 { float l; float4 v; float r; };
@@ -116,6 +142,7 @@ __device__ __forceinline__ void compute_tile(const UpdraftParams& p, const float
     const int rbase = r0 + 4 * warp;
     if (rbase >= p.rows) return;                      // warp-uniform
     const float* s = tile + (4 * warp) * SW;          // staged row index = (row - r0) + 1
+    const bool want_angles = (p.slope != nullptr) || (p.aspect != nullptr);
     Row6 below = load_row(s, lane);
     Row6 mid = load_row(s + SW, lane);
 #pragma unroll
@@ -153,8 +180,12 @@ __device__ __forceinline__ void compute_tile(const UpdraftParams& p, const float
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = c0 + j;
-                cell(S[j], S[j + 1], S[j + 2], M[j], M[j + 2], N[j], N[j + 1], N[j + 2],
-                     p.inv8res, V[j], sn[j], cs[j], sl[j], as[j], oro[j]);
+                if (want_angles)
+                    cell<true>(S[j], S[j + 1], S[j + 2], M[j], M[j + 2], N[j], N[j + 1], N[j + 2],
+                               p.inv8res, V[j], sn[j], cs[j], sl[j], as[j], oro[j]);
+                else
+                    cell<false>(S[j], S[j + 1], S[j + 2], M[j], M[j + 2], N[j], N[j + 1], N[j + 2],
+                                p.inv8res, V[j], sn[j], cs[j], sl[j], as[j], oro[j]);
                 if (edge_row || c == 0 || c >= p.cols - 1) { sl[j] = 0.0f; as[j] = 0.0f; oro[j] = 0.0f; }
                 up[j] = threshold_fn(oro[j], p.thr, p.thr_inv, p.inv_em1);
             }

@@ -181,13 +181,15 @@ def _f32_cuda(a, torch):
 def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, memory_parameter: int = 1,
                           scaling_parameter: float = 1.0, fields=None, updraft_field=None, potential_field=None,
                           seed: int = 0, track_id0: int = 0, uniforms=None, record: bool = False,
-                          traj_cap: Optional[int] = None, presence=None, total_steps=None) -> TrackBatchResult:
+                          traj_cap: Optional[int] = None, presence=None, total_steps=None,
+                          exact: bool = False) -> TrackBatchResult:
     """All tracks of one (case, realisation) in a single launch.
 
     `fields` is a pre-interleaved device tensor from `interleave_fields`; alternatively give
     `updraft_field` and `potential_field`; with neither the 'drw' model runs (reference :298-299).
     `uniforms` ([n_tracks, stride] float64) switches on verification mode; otherwise Philox keyed by
-    (seed, track_id0 + i, step).  `presence` (int32 CUDA tensor [rows, cols]) is accumulated into if given,
+    (seed, track_id0 + i, step).  `exact=True` forces the reference's exact operation order in production mode
+    (verification mode always uses it).  `presence` (int32 CUDA tensor [rows, cols]) is accumulated into if given,
     else a fresh raster is created.
     """
     torch = N.require_cuda()
@@ -228,7 +230,7 @@ def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, 
     N.check(lib.ssrs_step_tracks(N.ptr(fields), rows, cols, N.ptr(start), n, int(track_id0), dirp_c,
                                  int(memory_parameter), float(scaling_parameter), int(seed) & (2 ** 64 - 1),
                                  N.ptr(u_t), ustride, N.ptr(traj), cap, N.ptr(traj_len), N.ptr(presence),
-                                 N.ptr(total_steps), N.current_stream()), "ssrs_step_tracks")
+                                 N.ptr(total_steps), 1 if exact else 0, N.current_stream()), "ssrs_step_tracks")
     return TrackBatchResult(n, (rows, cols), traj, traj_len, presence, total_steps, cap)
 
 

@@ -50,7 +50,7 @@ def test_config1_end_to_end(tmp_path):
     from ssrs_b200.movmodel import get_starting_indices
     sr, sc = get_starting_indices(1000, (5, 55, 1, 2), "random", (60., 50.), 100.)
     ref = OC.step_tracks(up, pot, (500, 600), np.stack([sr, sc], 1), 0.0, 1, 1.0, seed=sim._track_seed(0, 0),
-                         traj_cap=int(lens.max()), nthreads=4)
+                         traj_cap=int(lens.max()), nthreads=4, fast=True)
     assert np.array_equal(ref["traj_len"], lens)
     assert np.array_equal(ref["presence"], sim.presence_counts())
     # "next" row: summary presence written with the reference's name and dtype

@@ -37,6 +37,17 @@ def test_golden_step_for_step(golden, name):
         assert np.array_equal(mm.compute_presence_counts(res.tracks(), g["U32"].shape), res.presence.cpu().numpy())
 
 
+def test_drw_philox():
+    from ssrs_b200 import movmodel as mm
+    n = 500
+    rng = np.random.RandomState(1)
+    starts = np.stack([rng.randint(2, 20, n), rng.randint(2, 98, n)], 1).astype(np.int32)
+    for dirn in (0.0, 30.0, 200.0):
+        ref = OC.step_tracks(None, None, (80, 100), starts, dirn, 1, 1.0, seed=5, fast=True)
+        res = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (80, 100), seed=5)
+        assert np.array_equal(res.presence.cpu().numpy(), ref["presence"]) and res.total_steps == ref["total_steps"]
+
+
 def test_drw_and_serial_api(golden):
     from ssrs_b200 import movmodel as mm
     g = golden("tracks")
@@ -64,10 +75,11 @@ def _fields(rows, cols, res, seed=1):
     return K.astype(np.float32)
 
 
-@pytest.mark.parametrize("mem,nu,dirn", [(1, 1.0, 0.0), (2, 1.0, 315.0), (0, 1.0, 0.0), (1, 2.0, 90.0)])
+@pytest.mark.parametrize("mem,nu,dirn", [(1, 1.0, 0.0), (2, 1.0, 315.0), (0, 1.0, 0.0), (1, 2.0, 90.0), (1, 0.0, 0.0)])
 def test_philox_matches_c_oracle(mem, nu, dirn):
     """Production mode: Philox streams keyed by (seed, track id, step) -> the C oracle reproduces every
-    trajectory and the presence raster bit for bit (3000 tracks on a 200x240 grid)."""
+    trajectory and the presence raster bit for bit (3000 tracks on a 200x240 grid), in the production
+    arithmetic and in the reference's exact operation order, and the two orders agree with each other."""
     from ssrs_b200 import movmodel as mm
     rows, cols = 200, 240
     U = _fields(rows, cols, 100.0)
@@ -76,9 +88,17 @@ def test_philox_matches_c_oracle(mem, nu, dirn):
     n = 3000
     starts = np.stack([rng.randint(2, 30, n), rng.randint(2, cols - 2, n)], 1).astype(np.int32)
     cap = 4 * max(rows, cols)
-    ref = OC.step_tracks(U, P, (rows, cols), starts, dirn, mem, nu, seed=1234, track_id0=17, traj_cap=cap, nthreads=8)
+    ref = OC.step_tracks(U, P, (rows, cols), starts, dirn, mem, nu, seed=1234, track_id0=17, traj_cap=cap, nthreads=8,
+                         fast=True)
     res = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, updraft_field=U,
                                    potential_field=P, seed=1234, track_id0=17, record=True, traj_cap=cap)
+    # the reference's exact operation order (numpy bit for bit) picks the same moves from the same streams
+    ref_exact = OC.step_tracks(U, P, (rows, cols), starts, dirn, mem, nu, seed=1234, track_id0=17, nthreads=8)
+    res_exact = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, updraft_field=U,
+                                         potential_field=P, seed=1234, track_id0=17, exact=True)
+    assert np.array_equal(res_exact.presence.cpu().numpy(), ref_exact["presence"])
+    assert np.array_equal(res_exact.traj_len.cpu().numpy(), ref_exact["traj_len"])
+    assert np.array_equal(ref_exact["presence"], ref["presence"])
     assert res.total_steps == ref["total_steps"]
     assert np.array_equal(res.traj_len.cpu().numpy(), ref["traj_len"])
     assert np.array_equal(res.presence.cpu().numpy(), ref["presence"])
@@ -138,7 +158,7 @@ def test_full_size_properties():
     assert lens.min() > 500 and total == int((lens.astype(np.int64) - 1).sum())
     m = 512
     ref = OC.step_tracks(up.cpu().numpy(), pot.cpu().numpy(), (rows, cols), np.stack([sr[:m], sc[:m]], 1), 0.0, 1, 1.0,
-                         seed=99, want_presence=False, nthreads=8)
+                         seed=99, want_presence=False, nthreads=8, fast=True)
     assert np.array_equal(lens[:m], ref["traj_len"])
 
 
