@@ -144,6 +144,10 @@ def build_fields_gpu(a, torch):
         except ImportError:
             solve_potential_device = None
         if solve_potential_device is not None:
+            # warm-up on a small grid: CUDA loads each kernel lazily on its first launch
+            zs = torch.from_numpy(synthetic_dem(256, 320, a.resolution, seed=1)).cuda()
+            ks = layers.updraft_fields(zs, a.resolution, 10.0, 270.0, 0.75, want=("updraft",))["updraft"]
+            solve_potential_device(ks, 0.0, strict=False)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             pot, stats = solve_potential_device(up, 0.0)

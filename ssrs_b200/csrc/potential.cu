@@ -83,6 +83,7 @@ SSRS_HD inline unsigned pair_hash(unsigned a, unsigned b) {
 struct FineGraph {
     const float* kd;     // conductivity with the sign bit marking Dirichlet nodes
     int rows, cols;
+    int interior_dirichlet;   // 1 if some Dirichlet node is more than one cell away from the border
     SSRS_HD i64 size() const { return (i64)rows * cols; }
     SSRS_HD bool excluded(i64 i) const { return sign_set(kd[i]); }
     SSRS_HD void range(i64, i64& k0, i64& k1) const { k0 = 0; k1 = 9; }
@@ -142,6 +143,83 @@ SSRS_HD inline void row_eval(const G& g, i64 i, const double* x, bool with_dir, 
     diag = d;
     const double excess = with_dir ? (d + offsum + dirsum) : (d + offsum);
     ax = excess * xi + s;
+}
+
+// ---- fine level, specialised ------------------------------------------------------------------------
+// The generic providers above are used for setup.  The cycle and Krylov kernels of the fine level (most of
+// the solve time) evaluate a cell's eight links with compile-time offsets instead.  FAST selects float32
+// link weights (one MUFU reciprocal per link) for the preconditioner, where exactness is not required;
+// the outer iteration always uses the float64 weights, so the solution is that of the exact operator.
+template <bool FAST>
+SSRS_HD inline double link_weight(float ka_raw, float kb_raw, bool diagonal) {
+    if (FAST) {
+        const float a = fabsf(ka_raw), b = fabsf(kb_raw);
+        float hm;
+        if (a == 0.0f || b == 0.0f) hm = 1e-08f;
+        else {
+#ifdef __CUDA_ARCH__
+            hm = __fdividef(2.0f * a * b, a + b);
+#else
+            hm = 2.0f * a * b / (a + b);
+#endif
+        }
+        return (double)(diagonal ? hm * 0.70710677f : hm);
+    } else {
+        const double a = fabs((double)ka_raw), b = fabs((double)kb_raw);
+        const double hm = (a == 0.0 || b == 0.0) ? HM_FLOOR : 2.0 * a * b / (a + b);
+        return diagonal ? hm * INV_SQRT2_F32 : hm;
+    }
+}
+
+// ax = (A x)_i and diag = a_ii for cell i of the fine grid.  WITH_DIR: Dirichlet neighbours contribute their
+// value (true operator); otherwise they only load the diagonal (error equation).
+template <bool FAST, bool WITH_DIR>
+SSRS_HD inline void fine_row(const FineGraph& g, i64 i, const double* x, double& ax, double& diag) {
+    const int cols = g.cols, rows = g.rows;
+    const int r = (int)(i / cols), c = (int)(i - (i64)r * cols);
+    const float kc = g.kd[i];
+    const double xi = x[i];
+    const bool quirk = (c == cols - 1) && (r >= 1) && (r <= rows - 2);     // movmodel.py:73-79
+    double s = 0.0, d = 0.0;
+#define SSRS_LINK(DR, DC)                                                                       \
+    if ((DR < 0 ? r > 0 : (DR > 0 ? r < rows - 1 : true)) && (DC < 0 ? c > 0 : (DC > 0 ? c < cols - 1 : true))) { \
+        const i64 j = i + (i64)(DR) * cols + (DC);                                              \
+        const float kj = g.kd[j];                                                               \
+        bool dg = (DR != 0) && (DC != 0);                                                       \
+        if (DR == -1 && DC == 0 && quirk) dg = true;                                            \
+        if (DR == -1 && DC == -1 && quirk) dg = false;                                          \
+        const double w = link_weight<FAST>(kc, kj, dg);                                         \
+        d += w;                                                                                 \
+        if (WITH_DIR || !sign_set(kj)) s += w * (xi - x[j]);                                    \
+    }
+    SSRS_LINK(-1, -1) SSRS_LINK(-1, 0) SSRS_LINK(-1, 1)
+    SSRS_LINK(0, -1)                    SSRS_LINK(0, 1)
+    SSRS_LINK(1, -1)  SSRS_LINK(1, 0)  SSRS_LINK(1, 1)
+#undef SSRS_LINK
+    // error equation: links to Dirichlet neighbours act on (x_i - 0)
+    if (!WITH_DIR) {
+        double ddir = 0.0;
+#define SSRS_DIRLINK(DR, DC)                                                                    \
+        if ((DR < 0 ? r > 0 : (DR > 0 ? r < rows - 1 : true)) && (DC < 0 ? c > 0 : (DC > 0 ? c < cols - 1 : true))) { \
+            const float kj = g.kd[i + (i64)(DR) * cols + (DC)];                                 \
+            if (sign_set(kj)) {                                                                 \
+                bool dg = (DR != 0) && (DC != 0);                                               \
+                if (DR == -1 && DC == 0 && quirk) dg = true;                                    \
+                if (DR == -1 && DC == -1 && quirk) dg = false;                                  \
+                ddir += link_weight<FAST>(kc, kj, dg);                                          \
+            }                                                                                   \
+        }
+        // Dirichlet nodes sit on the border only when produced by get_boundary_nodes; test cheaply
+        if (r <= 1 || c <= 1 || r >= rows - 2 || c >= cols - 2 || g.interior_dirichlet) {
+            SSRS_DIRLINK(-1, -1) SSRS_DIRLINK(-1, 0) SSRS_DIRLINK(-1, 1)
+            SSRS_DIRLINK(0, -1)                       SSRS_DIRLINK(0, 1)
+            SSRS_DIRLINK(1, -1)  SSRS_DIRLINK(1, 0)  SSRS_DIRLINK(1, 1)
+        }
+#undef SSRS_DIRLINK
+        s += ddir * xi;
+    }
+    ax = s;
+    diag = d;
 }
 
 // ---- storage ------------------------------------------------------------------------------------
@@ -417,6 +495,7 @@ struct Hierarchy {
     int coarse_sweeps = 0;     // > 0: coarsest level too large for a dense inverse, Jacobi sweeps instead
     double omega = 0.7;
     int nu = 2;
+    double* fres = nullptr;    // fine-level residual scratch
 };
 
 inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; return g; }
@@ -426,6 +505,48 @@ int smooth(const G g, const double* b, double*& x, double*& t, int sweeps, bool 
     for (int s = 0; s < sweeps; ++s) {
         if (s == 0 && zero_guess) { AMG_TRY(jacobi_first(g, b, x, omega, st)); }
         else { AMG_TRY(jacobi(g, b, x, t, omega, st)); double* sw = x; x = t; t = sw; }
+    }
+    return SSRS_OK;
+}
+
+// fine-level specialisations of the cycle kernels (float32 link weights: preconditioner only)
+inline int fine_jacobi_first(const FineGraph g, const double* b, double* x, double omega, stream_t st) {
+    return pfor(g.size(), st, [=] SSRS_HD(i64 i) {
+        if (g.excluded(i)) { x[i] = 0.0; return; }
+        double ax, d;
+        fine_row<true, false>(g, i, b, ax, d);        // only the diagonal is used
+        x[i] = omega * b[i] / d;
+    });
+}
+inline int fine_jacobi(const FineGraph g, const double* b, const double* x, double* xn, double omega, stream_t st) {
+    return pfor(g.size(), st, [=] SSRS_HD(i64 i) {
+        if (g.excluded(i)) { xn[i] = 0.0; return; }
+        double ax, d;
+        fine_row<true, false>(g, i, x, ax, d);
+        xn[i] = x[i] + omega * (b[i] - ax) / d;
+    });
+}
+// residual per cell (coalesced) into `res`, then a deterministic per-aggregate sum
+inline int fine_restrict_residual(const FineGraph g, const Level& L, const double* b, const double* x, double* res,
+                                  double* bc, stream_t st) {
+    if (pfor(g.size(), st, [=] SSRS_HD(i64 i) {
+            if (g.excluded(i)) { res[i] = 0.0; return; }
+            double ax, d;
+            fine_row<true, false>(g, i, x, ax, d);
+            res[i] = b[i] - ax;
+        }) != 0) return -1;
+    const i64* memptr = L.memptr; const int* mem = L.mem;
+    return pfor(L.nc, st, [=] SSRS_HD(i64 I) {
+        double s = 0.0;
+        for (i64 p = memptr[I]; p < memptr[I + 1]; ++p) s += res[mem[p]];
+        bc[I] = s;
+    });
+}
+inline int fine_smooth(const FineGraph g, const double* b, double*& x, double*& t, int sweeps, bool zero_guess,
+                       double omega, stream_t st) {
+    for (int s = 0; s < sweeps; ++s) {
+        if (s == 0 && zero_guess) { AMG_TRY(fine_jacobi_first(g, b, x, omega, st)); }
+        else { AMG_TRY(fine_jacobi(g, b, x, t, omega, st)); double* sw = x; x = t; t = sw; }
     }
     return SSRS_OK;
 }
@@ -445,11 +566,11 @@ int coarse_solve(Hierarchy& H, Level& C, stream_t st) {
 int vcycle(Hierarchy& H, const double* rhs, double*& out, double*& tmp, stream_t st) {
     const int nl = (int)H.lv.size();
     if (nl == 1) {          // no coarse level: plain Jacobi sweeps
-        return smooth(H.fine, rhs, out, tmp, 2 * H.nu, true, H.omega, st);
+        return fine_smooth(H.fine, rhs, out, tmp, 2 * H.nu, true, H.omega, st);
     }
-    int rc = smooth(H.fine, rhs, out, tmp, H.nu, true, H.omega, st);
+    int rc = fine_smooth(H.fine, rhs, out, tmp, H.nu, true, H.omega, st);
     if (rc) return rc;
-    AMG_TRY(restrict_residual(H.fine, H.lv[0], rhs, out, H.lv[1].b, st));
+    AMG_TRY(fine_restrict_residual(H.fine, H.lv[0], rhs, out, H.fres, H.lv[1].b, st));
     for (int l = 1; l < nl - 1; ++l) {
         Level& L = H.lv[l];
         rc = smooth(csr_of(L), L.b, L.x, L.t, H.nu, true, H.omega, st);
@@ -465,7 +586,7 @@ int vcycle(Hierarchy& H, const double* rhs, double*& out, double*& tmp, stream_t
         if (rc) return rc;
     }
     AMG_TRY(prolong_add(H.lv[0], H.fine.size(), out, H.lv[1].x, st));
-    return smooth(H.fine, rhs, out, tmp, H.nu, false, H.omega, st);
+    return fine_smooth(H.fine, rhs, out, tmp, H.nu, false, H.omega, st);
 }
 
 int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
@@ -501,7 +622,7 @@ int fine_residual(const FineGraph fg, const double* x, double* out, double* nrm2
     const i64 n = fg.size();
     AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
         if (fg.excluded(i)) { out[i] = 0.0; return; }
-        double ax, d; row_eval(fg, i, x, true, ax, d);
+        double ax, d; fine_row<false, true>(fg, i, x, ax, d);
         out[i] = -ax;
     }));
     AMG_TRY(preduce_sum(n, st, nrm2, [=] SSRS_HD(i64 i) { return out[i] * out[i]; }));
@@ -511,7 +632,7 @@ int fine_residual(const FineGraph fg, const double* x, double* out, double* nrm2
 int fine_apply(const FineGraph fg, const double* in, double* out, stream_t st) {
     AMG_TRY(pfor(fg.size(), st, [=] SSRS_HD(i64 i) {
         if (fg.excluded(i)) { out[i] = 0.0; return; }
-        double ax, d; row_eval(fg, i, in, false, ax, d);
+        double ax, d; fine_row<false, false>(fg, i, in, ax, d);
         out[i] = ax;
     }));
     return SSRS_OK;
@@ -580,7 +701,13 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         x[i] = d_bval[q];
     }));
     AMG_TRY(sync(st));
-    H.fine.kd = kd; H.fine.rows = rows; H.fine.cols = cols;
+    int interior = 0;
+    for (int64_t q = 0; q < n_bnodes; ++q) {
+        const int rr = bidx[(size_t)q] / cols, cc = bidx[(size_t)q] % cols;
+        if (rr > 0 && rr < rows - 1 && cc > 0 && cc < cols - 1) { interior = 1; break; }
+    }
+    H.fine.kd = kd; H.fine.rows = rows; H.fine.cols = cols; H.fine.interior_dirichlet = interior;
+    AMG_ALLOC(H.fres, double, n);
 
     // ---- setup: hierarchy ----
     const double theta = 0.5;

@@ -50,13 +50,27 @@ struct UpdraftParams {
     int vec_ok;            // cols % 4 == 0 and all pointers 16B aligned -> float4 global accesses
 };
 
+// raw MUFU approximations (<= 2 ulp, no denormal fix-up code around them)
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ float threshold_fn(float w, float thr, float thr_inv, float inv_em1) {
-    // layers.py:171-180: 0 if w <= 0.01 ; w if w > thr ; thr*(exp((w/thr)^5)-1)/(e-1) otherwise
+    // layers.py:171-180: 0 if w <= 0.01 ; w if w > thr ; thr*(exp((w/thr)^5)-1)/(e-1) otherwise.
+    // exp(x)-1 on (0,1] as x*P(x), degree-6 minimax fit, relative error 1.3e-7 (keeps the tiny values that
+    // act as insulating films in the potential solve accurate, which exp(x)-1 in float32 would not).
     if (!(w > 0.01f)) return 0.0f;
     if (w > thr) return w;
-    float t = w * thr_inv;
-    float t2 = t * t;
-    return thr * expm1f(t2 * t2 * t) * inv_em1;
+    const float t = w * thr_inv;
+    const float t2 = t * t;
+    const float x = t2 * t2 * t;
+    float p = 0.00031020541791804135f;
+    p = fmaf(p, x, 0.0012223972007632256f);
+    p = fmaf(p, x, 0.008451635017991066f);
+    p = fmaf(p, x, 0.041624147444963455f);
+    p = fmaf(p, x, 0.16667389869689941f);
+    p = fmaf(p, x, 0.4999995529651642f);
+    p = fmaf(p, x, 1.0f);
+    return thr * inv_em1 * (p * x);
 }
 
 // atan(t) for t in [0, 1]: t * P(t^2), degree-6 minimax fit (max error 3.2e-7 rad = 1.8e-5 degrees,
@@ -85,18 +99,18 @@ __device__ __forceinline__ void cell(float sw_, float sc_, float se_, float mw_,
     const float gx = ((ne_ - se_) + 2.0f * (nc_ - sc_) + (nw_ - sw_)) * inv8res;
     const float gy = ((se_ - sw_) + 2.0f * (me_ - mw_) + (ne_ - nw_)) * inv8res;
     const float h2 = fmaf(gx, gx, gy * gy);
-    const float h = h2 > 0.0f ? h2 * rsqrtf(h2) : 0.0f;
+    const float h = h2 > 1e-30f ? h2 * rsqrt_approx(h2) : 0.0f;
     const float gxa = (gx == 0.0f) ? 1e-10f : gx;                         // layers.py:124
-    const float rha = rsqrtf(fmaf(gxa, gxa, gy * gy));
+    const float rha = rsqrt_approx(fmaf(gxa, gxa, gy * gy));
     const float cosd = -(gy * cosw + gxa * sinw) * rha;                   // cos(aspect - wdir)
-    const float sins = h * rsqrtf(1.0f + h2);                             // sin(atan(h))
+    const float sins = h * rsqrt_approx(1.0f + h2);                             // sin(atan(h))
     oro = fmaxf(0.0f, V * sins * fmaxf(0.0f, cosd));                      // layers.py:19-22
     if (WANT_ANGLES) {
         const bool steep = h > 1.0f;
-        float a = atan01(steep ? __fdividef(1.0f, h) : h);
+        float a = atan01(steep ? rcp_approx(h) : h);
         slope = (steep ? 1.5707963267948966f - a : a) * 57.29577951308232f;
         const float ay = fabsf(gy), ax = fabsf(gxa);
-        float p = atan01(__fdividef(fminf(ay, ax), fmaxf(ay, ax)));
+        float p = atan01(fminf(ay, ax) * rcp_approx(fmaxf(ay, ax)));
         p = ay > ax ? 1.5707963267948966f - p : p;
         const float ang = ((gy < 0.0f) != (gxa < 0.0f)) ? -p : p;         // atan(dz_dy / dz_dx)
         aspect = 180.0f - ang * 57.29577951308232f + copysignf(90.0f, gxa);   // layers.py:125-127
@@ -244,7 +258,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(NTHREADS) updraft_tma_kernel(const UpdraftParams p,
+__global__ void __launch_bounds__(NTHREADS, 4) updraft_tma_kernel(const UpdraftParams p,
                                                                const __grid_constant__ CUtensorMap dem_map) {
     __shared__ __align__(128) float tiles[STAGES][TILE_STRIDE];
     __shared__ __align__(8) uint64_t full[STAGES];
@@ -355,8 +369,8 @@ extern "C" int ssrs_updraft(const float* dem, int rows, int cols, float resoluti
             set_error("ssrs_updraft: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
             return SSRS_ERR_CUDA;
         }
-        // persistent grid: a multiple of the SM count (3 CTAs/SM: 37 KB smem + 256 threads each)
-        int grid = sm_count() * 3;
+        // persistent grid: a multiple of the SM count (4 CTAs/SM: 37 KB smem, 256 threads, <= 64 registers each)
+        int grid = sm_count() * 4;
         if (grid > ntiles) grid = ntiles;
         updraft_tma_kernel<true><<<grid, NTHREADS, 0, st>>>(p, map);
     } else if (p.vec_ok) {
