@@ -27,6 +27,8 @@ def lib():
         _lib.oracle_presence_counts.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         _lib.oracle_philox_uniform.restype = C.c_double
         _lib.oracle_philox_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        _lib.oracle_philox_words.restype = None
+        _lib.oracle_philox_words.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
     return _lib
 
 
@@ -67,6 +69,12 @@ def presence_counts(traj, traj_len, shape):
     traj_len = np.ascontiguousarray(traj_len, dtype=np.int32)
     out = np.zeros((rows, cols), dtype=np.int32)
     lib().oracle_presence_counts(_ptr(traj), traj.shape[1], _ptr(traj_len), traj.shape[0], rows, cols, _ptr(out))
+    return out
+
+
+def philox_words(seed, track, block):
+    out = np.zeros(4, dtype=np.uint32)
+    lib().oracle_philox_words(int(seed), int(track), int(block), _ptr(out))
     return out
 
 

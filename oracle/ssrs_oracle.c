@@ -23,7 +23,7 @@
 static const unsigned RESTRICT_LUT[9] = {0x00B, 0x007, 0x026, 0x049, 0x1EF, 0x124, 0x0C8, 0x1C0, 0x1A0};
 
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                          uint32_t* o0, uint32_t* o1) {
+                          uint32_t* o) {
     for (int i = 0; i < 10; ++i) {
         uint64_t m0 = (uint64_t)0xD2511F53u * c0, m1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(m1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)m1;
@@ -31,13 +31,24 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    *o0 = c0; *o1 = c1;
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+/* Uniform for step `step` of track `track`: Philox4x32-10 with counter (track, step >> 1) and key = seed yields
+ * four words = two uniforms (words {0,1} for even steps, {2,3} for odd steps); 52 mantissa bits -> [0,1).
+ * Same construction as ssrs_b200/csrc/tracks.cu. */
 double oracle_philox_uniform(uint64_t seed, uint64_t track, uint32_t step) {
-    uint32_t a, b;
-    philox4x32_10((uint32_t)track, (uint32_t)(track >> 32), step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), &a, &b);
-    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    uint32_t w[4];
+    philox4x32_10((uint32_t)track, (uint32_t)(track >> 32), step >> 1, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    const uint32_t a = w[2 * (step & 1u)], b = w[2 * (step & 1u) + 1];
+    const uint64_t bits = 0x3FF0000000000000ULL | ((uint64_t)a << 20) | (uint64_t)(b >> 12);
+    double d;
+    memcpy(&d, &bits, 8);
+    return d - 1.0;
+}
+
+void oracle_philox_words(uint64_t seed, uint64_t track, uint32_t block, uint32_t* out4) {
+    philox4x32_10((uint32_t)track, (uint32_t)(track >> 32), block, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), out4);
 }
 
 static double pairwise9(const double* p) {
@@ -101,9 +112,51 @@ static int choose_exact(const float* U, const float* P, int nc, int r, int c, co
  * and the move is the first index whose running sum exceeds u * sum(q).  Same distribution as choose_exact up to
  * rounding of the cdf boundaries; restated here operation for operation so GPU production runs can be checked
  * bit for bit on the CPU.  Only mask-allowed neighbours are evaluated (also for the NaN test). */
+static const int CAND3[9][3] = {{0, 1, 3}, {0, 1, 2}, {1, 2, 5}, {0, 3, 6}, {-1, -1, -1}, {2, 5, 8}, {3, 6, 7}, {6, 7, 8}, {5, 7, 8}};
+
 static int choose_fast(const float* U, const float* P, int nc, int r, int c, const double* dirp, unsigned mask,
-                       double nu, double u) {
+                       double nu, double u, int last) {
     const float ninv_d = 0.70710677f;
+    if (last != 4 && nu == 1.0) {
+        /* three-candidate step, division-free: q_i ~ (d_i u_i) (s_a s_b), s_j = u_c + u_j, {a,b} the other two */
+        const int* ci = CAND3[last];
+        const int64_t o = (int64_t)r * nc + c;
+        double q3[3] = {0.0, 0.0, 0.0};
+        int en[3], nan3 = 0;
+        for (int j = 0; j < 3; ++j) en[j] = (mask >> ci[j]) & 1u;
+        if (U != NULL) {
+            double uc = (double)U[o]; if (uc < 1e-06) uc = 1e-06;
+            double uu[3], ss[3]; float dd[3];
+            for (int j = 0; j < 3; ++j) {
+                const int dr = ci[j] / 3 - 1, dc = ci[j] % 3 - 1;
+                const int64_t qn = o + (int64_t)dr * nc + dc;
+                const float ninv = (dr != 0 && dc != 0) ? ninv_d : 1.0f;
+                dd[j] = (float)(P[o] - P[qn]) * ninv;
+                if (en[j] && dd[j] != dd[j]) nan3 = 1;
+                uu[j] = (double)U[qn]; if (uu[j] < 1e-06) uu[j] = 1e-06;
+                ss[j] = uc + uu[j];
+            }
+            if (en[0] && dd[0] > 0.0f) q3[0] = ((double)dd[0] * uu[0]) * (ss[1] * ss[2]);
+            if (en[1] && dd[1] > 0.0f) q3[1] = ((double)dd[1] * uu[1]) * (ss[0] * ss[2]);
+            if (en[2] && dd[2] > 0.0f) q3[2] = ((double)dd[2] * uu[2]) * (ss[0] * ss[1]);
+        } else {
+            for (int j = 0; j < 3; ++j) q3[j] = en[j] ? dirp[ci[j]] : 0.0;
+        }
+        int fall = 0;
+        if (nan3 || (q3[0] == 0.0 && q3[1] == 0.0 && q3[2] == 0.0)) {
+            for (int j = 0; j < 3; ++j) q3[j] = en[j] ? dirp[ci[j]] : 0.0;
+            if (q3[0] == 0.0 && q3[1] == 0.0 && q3[2] == 0.0) fall = 1;
+        }
+        if (!fall) {
+            const double c0 = q3[0], c1 = c0 + q3[1], c2 = c1 + q3[2];
+            const double target = u * c2;
+            if (c0 > target) return ci[0];
+            if (c1 > target) return ci[1];
+            if (c2 > target) return ci[2];
+            return q3[2] > 0.0 ? ci[2] : (q3[1] > 0.0 ? ci[1] : ci[0]);
+        }
+        U = NULL; P = NULL; mask = 0u;          /* unmasked directional weights through the general path */
+    }
     double q[9];
     int any_nan = 0, nz = 0;
     const int64_t o = (int64_t)r * nc + c;
@@ -181,7 +234,7 @@ static int64_t one_track(const float* U, const float* P, int nr, int nc, int row
         }
         const double u = uniforms ? uniforms[k] : oracle_philox_uniform(seed, gid, (uint32_t)k);
         int idx;
-        if (fast) idx = choose_fast(U, P, nc, r, c, dirp, mask, nu, u);
+        if (fast) idx = choose_fast(U, P, nc, r, c, dirp, mask, nu, u, (int)hist[hist_len - 1]);
         else idx = choose_exact(U, P, nc, r, c, dirp, mask, nu, u);
         row = r + (idx / 3 - 1);                                       /* :313-317 */
         col = c + (idx % 3 - 1);

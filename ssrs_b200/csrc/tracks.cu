@@ -51,7 +51,7 @@ struct TrackParams {
 
 // Philox4x32-10 (Salmon et al. 2011), counter = (track_lo, track_hi, step_lo, step_hi), key = seed.
 __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                              unsigned k1, unsigned& o0, unsigned& o1) {
+                                              unsigned k1, unsigned& o0, unsigned& o1, unsigned& o2, unsigned& o3) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -60,12 +60,13 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    o0 = c0; o1 = c1;
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-__device__ __forceinline__ double uniform53(unsigned a, unsigned b) {
-    // numpy's random_sample recipe: 27 + 26 random bits -> [0,1)
-    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+__device__ __forceinline__ double uniform52(unsigned a, unsigned b) {
+    // 52 random mantissa bits under exponent 0 give [1,2); subtract 1 -> [0,1) on a 2^-52 lattice
+    const unsigned long long bits = 0x3FF0000000000000ULL | ((unsigned long long)a << 20) | (unsigned long long)(b >> 12);
+    return __longlong_as_double((long long)bits) - 1.0;
 }
 
 __device__ __forceinline__ double pairwise9(const double* p) {
@@ -200,20 +201,36 @@ __device__ __noinline__ int choose_fast_general(const TrackParams& P, const floa
 constexpr unsigned long long C3_A = (0x310ULL) | (0x210ULL << 12) | (0x521ULL << 24) | (0x630ULL << 36) | (0x000ULL << 48);
 constexpr unsigned long long C3_B = (0x852ULL) | (0x763ULL << 12) | (0x876ULL << 24) | (0x875ULL << 36);
 
+// Three-candidate step (every step after a track's first, nu == 1).  Division-free: with s_j = u_c + u_j,
+//   q_i = max(d_i, 0) u_i / s_i   is proportional to   (d_i u_i) * (s_a s_b),  {a, b} = the other two candidates,
+// so the weights need 3 adds and 9 multiplies.  f0..f2 are the candidates' {updraft, potential} pairs in
+// ascending flat-index order, already loaded by the caller (so the loads overlap the Philox rounds).
 template <bool HAS_FIELDS>
-__device__ __forceinline__ int choose_fast(const TrackParams& P, const float2* base, int nc, unsigned mask,
-                                           unsigned last, double u) {
-    if (last == 4u || !P.nu_is_one) return choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
-    const unsigned c3 = (unsigned)((last < 5 ? (C3_A >> (12 * last)) : (C3_B >> (12 * (last - 5)))) & 0xFFFu);
-    const int i0 = c3 & 15, i1 = (c3 >> 4) & 15, i2 = (c3 >> 8) & 15;
+__device__ __forceinline__ int choose_fast3(const TrackParams& P, const float2* base, int nc, unsigned mask,
+                                            int i0, int i1, int i2, float2 fc, float2 f0, float2 f1, float2 f2,
+                                            double u) {
     const bool e0 = (mask >> i0) & 1u, e1 = (mask >> i1) & 1u, e2 = (mask >> i2) & 1u;
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
     bool any_nan = false;
-    float2 fc = make_float2(0.f, 0.f);
-    double uc = 0.0;
-    if (HAS_FIELDS) { fc = __ldg(base); uc = fmax((double)fc.x, 1e-06); }
-    double q0 = e0 ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i0, any_nan) : 0.0;
-    double q1 = e1 ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i1, any_nan) : 0.0;
-    double q2 = e2 ? weight_fast<HAS_FIELDS>(P, base, fc, uc, nc, i2, any_nan) : 0.0;
+    if (HAS_FIELDS) {
+        const float n0 = ((i0 & 1) == 0) ? 0.70710677f : 1.0f;      // even flat index (0,2,6,8) = diagonal move
+        const float n1 = ((i1 & 1) == 0) ? 0.70710677f : 1.0f;
+        const float n2 = ((i2 & 1) == 0) ? 0.70710677f : 1.0f;
+        const float d0 = __fmul_rn(__fsub_rn(fc.y, f0.y), n0);      // float32, movmodel.py:301-304
+        const float d1 = __fmul_rn(__fsub_rn(fc.y, f1.y), n1);
+        const float d2 = __fmul_rn(__fsub_rn(fc.y, f2.y), n2);
+        any_nan = (e0 && d0 != d0) || (e1 && d1 != d1) || (e2 && d2 != d2);
+        const double uc = fmax((double)fc.x, 1e-06);
+        const double u0 = fmax((double)f0.x, 1e-06), u1 = fmax((double)f1.x, 1e-06), u2 = fmax((double)f2.x, 1e-06);
+        const double s0 = uc + u0, s1 = uc + u1, s2 = uc + u2;
+        if (e0 && d0 > 0.0f) q0 = ((double)d0 * u0) * (s1 * s2);
+        if (e1 && d1 > 0.0f) q1 = ((double)d1 * u1) * (s0 * s2);
+        if (e2 && d2 > 0.0f) q2 = ((double)d2 * u2) * (s0 * s1);
+    } else {
+        q0 = e0 ? P.dirp[i0] : 0.0;
+        q1 = e1 ? P.dirp[i1] : 0.0;
+        q2 = e2 ? P.dirp[i2] : 0.0;
+    }
     if (any_nan || (q0 == 0.0 && q1 == 0.0 && q2 == 0.0)) {
         q0 = e0 ? P.dirp[i0] : 0.0;
         q1 = e1 ? P.dirp[i1] : 0.0;
@@ -239,6 +256,7 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
     unsigned long long hist = 4;          // 4-bit move codes, most recent in the low nibble
     int hcount = 1;
     unsigned run_mask = 0x1EF;            // AND over the whole history (memory == 0)
+    unsigned rng_c = 0, rng_d = 0;        // second half of the last Philox block
 
     while (true) {
         if (!alive) {
@@ -276,20 +294,41 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
             int m = P.memory < hcount ? P.memory : hcount;
             for (int j = 0; j < m; ++j) mask &= restrict_mask((unsigned)((hist >> (4 * j)) & 15));
         }
+        const float2* base = HAS_FIELDS ? P.fields + (long long)r * nc + c : nullptr;
+        const bool three = !EXACT && last != 4u && P.nu_is_one;
+        // issue the gathers first so they overlap the random-number rounds
+        int i0 = 0, i1 = 0, i2 = 0;
+        float2 fc = make_float2(0.f, 0.f), f0 = fc, f1 = fc, f2 = fc;
+        if (three) {
+            const unsigned c3 = (unsigned)((last < 5 ? (C3_A >> (12 * last)) : (C3_B >> (12 * (last - 5)))) & 0xFFFu);
+            i0 = c3 & 15; i1 = (c3 >> 4) & 15; i2 = (c3 >> 8) & 15;
+            if (HAS_FIELDS) {
+                fc = __ldg(base);
+                f0 = __ldg(base + (i0 / 3 - 1) * nc + (i0 % 3 - 1));
+                f1 = __ldg(base + (i1 / 3 - 1) * nc + (i1 % 3 - 1));
+                f2 = __ldg(base + (i2 / 3 - 1) * nc + (i2 % 3 - 1));
+            }
+        }
         // one uniform per step (:312)
         double u;
         if (P.uniforms != nullptr) {
             u = __ldg(P.uniforms + t * P.ustride + k);
         } else {
-            const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
-            unsigned a, b;
-            philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)k, 0u, (unsigned)P.seed,
-                          (unsigned)(P.seed >> 32), a, b);
-            u = uniform53(a, b);
+            // Philox4x32-10 yields four words = two uniforms: counter (gid, k >> 1), words {0,1} for even k, {2,3} for odd k
+            if ((k & 1) == 0) {
+                const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
+                unsigned a, b;
+                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, (unsigned)P.seed,
+                              (unsigned)(P.seed >> 32), a, b, rng_c, rng_d);
+                u = uniform52(a, b);
+            } else {
+                u = uniform52(rng_c, rng_d);
+            }
         }
-        const float2* base = HAS_FIELDS ? P.fields + (long long)r * nc + c : nullptr;
-        const int idx = EXACT ? choose_exact<HAS_FIELDS>(P, base, nc, mask, u)
-                              : choose_fast<HAS_FIELDS>(P, base, nc, mask, last, u);
+        int idx;
+        if (EXACT) idx = choose_exact<HAS_FIELDS>(P, base, nc, mask, u);
+        else if (three) idx = choose_fast3<HAS_FIELDS>(P, base, nc, mask, i0, i1, i2, fc, f0, f1, f2, u);
+        else idx = choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
         row = r + (idx / 3 - 1);                                            // :313-317
         col = c + (idx % 3 - 1);
         ++k;

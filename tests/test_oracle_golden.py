@@ -122,11 +122,14 @@ def test_presence_and_smoothing(golden):
 
 
 def test_philox_known_answer():
-    """Philox4x32-10 known-answer vectors from the Random123 distribution (kat_vectors):
-    counter/key all zero -> 6627e8d5 e169c58d ... ; all ones -> 408f276d 41c83b0e ..."""
-    lib = OC.lib()
-    import ctypes as C
-    # the oracle exposes only the uniform; rebuild the first two words from it
-    u = lib.oracle_philox_uniform(0, 0, 0)
-    a, b = 0x6627e8d5, 0xe169c58d
-    assert u == ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0
+    """Philox4x32-10 known-answer vectors from the Random123 distribution (kat_vectors): counter/key all zero ->
+    6627e8d5 e169c58d bc57ac4c 9b00dbd8; all ones -> 408f276d 41c83b0e a20bc7c6 6d5451fd;
+    counter 243f6a88 85a308d3 13198a2e 03707344, key a4093822 299f31d0 -> d16cfe09 94fdcceb 5001e420 24126ea1."""
+    assert [hex(v) for v in OC.philox_words(0, 0, 0)] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    # step -> (block = step >> 1, word pair = step & 1), 52 mantissa bits
+    for step, (a, b) in enumerate([(0x6627e8d5, 0xe169c58d), (0xbc57ac4c, 0x9b00dbd8)]):
+        bits = 0x3FF0000000000000 | (a << 20) | (b >> 12)
+        expect = np.array([bits], dtype=np.uint64).view(np.float64)[0] - 1.0
+        assert OC.philox_uniform(0, 0, step) == expect
+    u = np.array([OC.philox_uniform(7, t, s) for t in range(50) for s in range(40)])
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.03
