@@ -46,7 +46,7 @@ struct TrackParams {
     double dirp[9];
     double nu;
     double max_moves;
-    int rows, cols, burnin, memory, nu_is_one;
+    int rows, cols, burnin, memory, nu_is_one, kmax;
 };
 
 // Philox4x32-10 (Salmon et al. 2011), counter = (track_lo, track_hi, step_lo, step_hi), key = seed.
@@ -205,11 +205,11 @@ constexpr unsigned long long C3_B = (0x852ULL) | (0x763ULL << 12) | (0x876ULL <<
 //   q_i = max(d_i, 0) u_i / s_i   is proportional to   (d_i u_i) * (s_a s_b),  {a, b} = the other two candidates,
 // so the weights need 3 adds and 9 multiplies.  f0..f2 are the candidates' {updraft, potential} pairs in
 // ascending flat-index order, already loaded by the caller (so the loads overlap the Philox rounds).
-template <bool HAS_FIELDS>
+template <bool HAS_FIELDS, bool MEM1>
 __device__ __forceinline__ int choose_fast3(const TrackParams& P, const float2* base, int nc, unsigned mask,
                                             int i0, int i1, int i2, float2 fc, float2 f0, float2 f1, float2 f2,
                                             double u) {
-    const bool e0 = (mask >> i0) & 1u, e1 = (mask >> i1) & 1u, e2 = (mask >> i2) & 1u;
+    const bool e0 = MEM1 || ((mask >> i0) & 1u), e1 = MEM1 || ((mask >> i1) & 1u), e2 = MEM1 || ((mask >> i2) & 1u);
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
     bool any_nan = false;
     if (HAS_FIELDS) {
@@ -245,15 +245,29 @@ __device__ __forceinline__ int choose_fast3(const TrackParams& P, const float2* 
     return q2 > 0.0 ? i2 : (q1 > 0.0 ? i1 : i0);
 }
 
-template <bool HAS_FIELDS, bool EXACT>
+// MEM1: track_dirn_restrict == 1 (the default): the mask is exactly the three candidates of the last move, so
+// no history register, no mask arithmetic.
+template <bool HAS_FIELDS, bool EXACT, bool MEM1>
 __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P) {
+    // per previous move: element offsets of its three candidates and their packed flat indices
+    __shared__ int4 s_cand[9];
+    if (threadIdx.x < 9) {
+        const unsigned last = threadIdx.x;
+        const unsigned c3 = (unsigned)((last < 5 ? (C3_A >> (12 * last)) : (C3_B >> (12 * (last - 5)))) & 0xFFFu);
+        const int i0 = c3 & 15, i1 = (c3 >> 4) & 15, i2 = (c3 >> 8) & 15;
+        s_cand[last] = make_int4((i0 / 3 - 1) * P.cols + (i0 % 3 - 1), (i1 / 3 - 1) * P.cols + (i1 % 3 - 1),
+                                 (i2 / 3 - 1) * P.cols + (i2 % 3 - 1), (int)c3);
+    }
+    __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nr = P.rows, nc = P.cols;
+    const int kmax = P.kmax;
     unsigned long long steps_local = 0;
     bool alive = false;
     int row = 0, col = 0, k = 0;
-    unsigned long long hist = 4;          // 4-bit move codes, most recent in the low nibble
+    unsigned last = 4;                    // flat index of the previous move (4 = none yet)
+    unsigned long long hist = 4;          // 4-bit move codes, most recent in the low nibble (only if !MEM1)
     int hcount = 1;
     unsigned run_mask = 0x1EF;            // AND over the whole history (memory == 0)
     unsigned rng_c = 0, rng_d = 0;        // second half of the last Philox block
@@ -262,13 +276,13 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
         if (!alive) {
             if (t >= P.n_tracks) break;
             int2 s = __ldg(P.start + t);
-            row = s.x; col = s.y; k = 0; hist = 4; hcount = 1; run_mask = 0x1EF;
+            row = s.x; col = s.y; k = 0; last = 4; hist = 4; hcount = 1; run_mask = 0x1EF;
             if (P.traj != nullptr && P.traj_cap > 0) P.traj[t] = make_short2((short)row, (short)col);
             if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
             alive = true;
         }
         int r = row, c = col;
-        bool finish = !((double)k < P.max_moves);                           // movmodel.py:285
+        bool finish = k >= kmax;                                            // movmodel.py:285
         if (!finish) {
             if (k > P.burnin) {                                             // :287-289
                 finish = !(0 < r && r < nr - 1 && 0 < c && c < nc - 1);
@@ -284,30 +298,29 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
             t += stride;
             continue;
         }
+        const int lin = r * nc + c;                                         // rows * cols < 2^31 (checked on the host)
+        const float2* base = HAS_FIELDS ? P.fields + lin : nullptr;
+        const bool three = !EXACT && last != 4u && P.nu_is_one;
+        // issue the gathers first so they overlap the random-number rounds
+        int4 cand = make_int4(0, 0, 0, 0);
+        float2 fc = make_float2(0.f, 0.f), f0 = fc, f1 = fc, f2 = fc;
+        if (three) {
+            cand = s_cand[last];
+            if (HAS_FIELDS) {
+                fc = __ldg(base);
+                f0 = __ldg(base + cand.x);
+                f1 = __ldg(base + cand.y);
+                f2 = __ldg(base + cand.z);
+            }
+        }
         // direction-memory mask (:307-309)
-        const unsigned last = (unsigned)(hist & 15);
         unsigned mask;
-        if (P.memory == 1) mask = restrict_mask(last);
+        if (MEM1) mask = (three ? 0u : restrict_mask(last));
         else if (P.memory == 0) mask = run_mask;
         else {
             mask = 0x1EF;
             int m = P.memory < hcount ? P.memory : hcount;
             for (int j = 0; j < m; ++j) mask &= restrict_mask((unsigned)((hist >> (4 * j)) & 15));
-        }
-        const float2* base = HAS_FIELDS ? P.fields + (long long)r * nc + c : nullptr;
-        const bool three = !EXACT && last != 4u && P.nu_is_one;
-        // issue the gathers first so they overlap the random-number rounds
-        int i0 = 0, i1 = 0, i2 = 0;
-        float2 fc = make_float2(0.f, 0.f), f0 = fc, f1 = fc, f2 = fc;
-        if (three) {
-            const unsigned c3 = (unsigned)((last < 5 ? (C3_A >> (12 * last)) : (C3_B >> (12 * (last - 5)))) & 0xFFFu);
-            i0 = c3 & 15; i1 = (c3 >> 4) & 15; i2 = (c3 >> 8) & 15;
-            if (HAS_FIELDS) {
-                fc = __ldg(base);
-                f0 = __ldg(base + (i0 / 3 - 1) * nc + (i0 % 3 - 1));
-                f1 = __ldg(base + (i1 / 3 - 1) * nc + (i1 % 3 - 1));
-                f2 = __ldg(base + (i2 / 3 - 1) * nc + (i2 % 3 - 1));
-            }
         }
         // one uniform per step (:312)
         double u;
@@ -327,17 +340,24 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
         }
         int idx;
         if (EXACT) idx = choose_exact<HAS_FIELDS>(P, base, nc, mask, u);
-        else if (three) idx = choose_fast3<HAS_FIELDS>(P, base, nc, mask, i0, i1, i2, fc, f0, f1, f2, u);
-        else idx = choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
-        row = r + (idx / 3 - 1);                                            // :313-317
-        col = c + (idx % 3 - 1);
+        else if (three) {
+            const int i0 = cand.w & 15, i1 = (cand.w >> 4) & 15, i2 = (cand.w >> 8) & 15;
+            idx = choose_fast3<HAS_FIELDS, MEM1>(P, base, nc, mask, i0, i1, i2, fc, f0, f1, f2, u);
+        } else idx = choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
+        const int dr = ((idx * 11) >> 5) - 1;                               // idx / 3 - 1 for idx in 0..8
+        const int dc = idx - 3 * (dr + 1) - 1;
+        row = r + dr;                                                       // :313-317
+        col = c + dc;
         ++k;
-        hist = (hist << 4) | (unsigned long long)idx;
-        hcount = hcount < 16 ? hcount + 1 : 16;
-        run_mask &= restrict_mask((unsigned)idx);
+        last = (unsigned)idx;
+        if (!MEM1) {
+            hist = (hist << 4) | (unsigned long long)idx;
+            hcount = hcount < 16 ? hcount + 1 : 16;
+            run_mask &= restrict_mask((unsigned)idx);
+        }
         if (P.traj != nullptr && (long long)k < P.traj_cap)
             P.traj[(long long)k * P.n_tracks + t] = make_short2((short)row, (short)col);
-        if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
+        if (P.presence != nullptr) atomicAdd(P.presence + (lin + dr * nc + dc), 1u);
     }
     if (P.total_steps != nullptr) {
         // one atomic per warp
@@ -381,6 +401,7 @@ extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const i
                                 int flags, void* stream) {
     SSRS_REQUIRE(rows >= 5 && cols >= 5, "ssrs_step_tracks: grid %dx%d too small", rows, cols);
     SSRS_REQUIRE(rows <= 32767 && cols <= 32767, "ssrs_step_tracks: int16 trajectories need rows, cols <= 32767");
+    SSRS_REQUIRE((long long)rows * cols < 2147483647LL, "ssrs_step_tracks: more than 2^31 cells");
     SSRS_REQUIRE(n_tracks >= 0 && track_id0 >= 0, "ssrs_step_tracks: negative track count or id");
     SSRS_REQUIRE(start_rc != nullptr || n_tracks == 0, "ssrs_step_tracks: start_rc is NULL");
     SSRS_REQUIRE(dirprob9_host != nullptr, "ssrs_step_tracks: dirprob9_host is NULL");
@@ -404,15 +425,25 @@ extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const i
     for (int i = 0; i < 9; ++i) P.dirp[i] = dirprob9_host[i];
     P.nu = nu; P.nu_is_one = (nu == 1.0);
     P.max_moves = (double)rows / 2 * (double)cols / 2;                       // movmodel.py:277
+    {   // `k < max_moves` with integer k  <=>  k < ceil(max_moves)
+        const double km = ceil(P.max_moves);
+        P.kmax = km > 2147483647.0 ? 2147483647 : (int)km;
+    }
     P.rows = rows; P.cols = cols;
     P.burnin = (int)((rows < cols ? rows : cols) / 10);                      // movmodel.py:276
     P.memory = memory;
     // verification mode always uses the exact (numpy bit-for-bit) arithmetic
     const bool exact = (uniforms != nullptr) || (flags & SSRS_STEP_EXACT);
     const int threads = 128;
-    void (*kern)(const TrackParams) =
-        fields != nullptr ? (exact ? step_tracks_kernel<true, true> : step_tracks_kernel<true, false>)
-                          : (exact ? step_tracks_kernel<false, true> : step_tracks_kernel<false, false>);
+    const bool mem1 = (memory == 1);
+    void (*kern)(const TrackParams);
+    if (fields != nullptr) {
+        if (exact) kern = mem1 ? step_tracks_kernel<true, true, true> : step_tracks_kernel<true, true, false>;
+        else kern = mem1 ? step_tracks_kernel<true, false, true> : step_tracks_kernel<true, false, false>;
+    } else {
+        if (exact) kern = mem1 ? step_tracks_kernel<false, true, true> : step_tracks_kernel<false, true, false>;
+        else kern = mem1 ? step_tracks_kernel<false, false, true> : step_tracks_kernel<false, false, false>;
+    }
     // as many tracks resident at once as the registers allow: the kernel is latency-bound and its duration is
     // set by the longest track, so every track should start at time zero
     int per_sm = 0;
