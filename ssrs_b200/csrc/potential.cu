@@ -222,6 +222,53 @@ SSRS_HD inline void fine_row(const FineGraph& g, i64 i, const double* x, double&
     diag = d;
 }
 
+// Precomputed forward link weights (E, N, NE, NW of every cell; 0 where the neighbour is outside the grid) in
+// float32 (preconditioner) and float64 (exact operator).  A cell's other four links are its neighbours'
+// forward links — except on the reference's quirk column (last column, interior rows) whose S and SW links
+// carry swapped distance factors and are evaluated from K directly.  All eight neighbours are included: for
+// error-equation vectors the caller keeps x = 0 at Dirichlet nodes, which is exactly "only load the diagonal".
+struct FineWeights {
+    const float* wf;    // [4][n]
+    const double* wd;   // [4][n]
+};
+
+template <bool FAST>
+SSRS_HD inline void fine_row_w(const FineGraph& g, const FineWeights& W, i64 i, const double* x, double& ax, double& diag) {
+    const i64 n = (i64)g.rows * g.cols;
+    const int cols = g.cols;
+    const int r = (int)(i / cols), c = (int)(i - (i64)r * cols);
+    const double xi = x[i];
+    double s = 0.0, d = 0.0;
+    // backward neighbours index below i, forward above; clamp so that zero-weight out-of-grid links stay in bounds
+    const i64 jW = i - 1 < 0 ? 0 : i - 1, jS = i - cols < 0 ? 0 : i - cols;
+    const i64 jSW = i - cols - 1 < 0 ? 0 : i - cols - 1, jSE = i - cols + 1 < 0 ? 0 : i - cols + 1;
+    const i64 jE = i + 1 >= n ? n - 1 : i + 1, jN = i + cols >= n ? n - 1 : i + cols;
+    const i64 jNE = i + cols + 1 >= n ? n - 1 : i + cols + 1, jNW = i + cols - 1 >= n ? n - 1 : i + cols - 1;
+    double wE, wN, wNE, wNW, wW, wS, wSW, wSE;
+    if (FAST) {
+        const float* w = W.wf;
+        wE = w[i]; wN = w[n + i]; wNE = w[2 * n + i]; wNW = w[3 * n + i];
+        wW = (i - 1 >= 0) ? w[jW] : 0.0f; wS = (i - cols >= 0) ? w[n + jS] : 0.0f;
+        wSW = (i - cols - 1 >= 0) ? w[2 * n + jSW] : 0.0f; wSE = (i - cols + 1 >= 0) ? w[3 * n + jSE] : 0.0f;
+    } else {
+        const double* w = W.wd;
+        wE = w[i]; wN = w[n + i]; wNE = w[2 * n + i]; wNW = w[3 * n + i];
+        wW = (i - 1 >= 0) ? w[jW] : 0.0; wS = (i - cols >= 0) ? w[n + jS] : 0.0;
+        wSW = (i - cols - 1 >= 0) ? w[2 * n + jSW] : 0.0; wSE = (i - cols + 1 >= 0) ? w[3 * n + jSE] : 0.0;
+    }
+    if (c == cols - 1 && r >= 1 && r <= g.rows - 2) {                       // movmodel.py:73-79
+        wS = link_weight<FAST>(g.kd[i], g.kd[i - cols], true);
+        wSW = link_weight<FAST>(g.kd[i], g.kd[i - cols - 1], false);
+    }
+    // a cell in column 0 must not see its "W" neighbour's wrapped weight: forward weights of out-of-grid links
+    // are stored as 0, and W of column 0 reads the E weight of the previous row's last cell, which is 0.
+    d = ((wE + wW) + (wN + wS)) + ((wNE + wSW) + (wNW + wSE));
+    s = wE * (xi - x[jE]) + wW * (xi - x[jW]) + wN * (xi - x[jN]) + wS * (xi - x[jS]) +
+        wNE * (xi - x[jNE]) + wSW * (xi - x[jSW]) + wNW * (xi - x[jNW]) + wSE * (xi - x[jSE]);
+    ax = s;
+    diag = d;
+}
+
 // ---- storage ------------------------------------------------------------------------------------
 struct Pool {
     std::vector<void*> ptrs;
@@ -496,6 +543,7 @@ struct Hierarchy {
     double omega = 0.7;
     int nu = 2;
     double* fres = nullptr;    // fine-level residual scratch
+    FineWeights fw = {nullptr, nullptr};
 };
 
 inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; return g; }
@@ -510,29 +558,29 @@ int smooth(const G g, const double* b, double*& x, double*& t, int sweeps, bool 
 }
 
 // fine-level specialisations of the cycle kernels (float32 link weights: preconditioner only)
-inline int fine_jacobi_first(const FineGraph g, const double* b, double* x, double omega, stream_t st) {
+inline int fine_jacobi_first(const FineGraph g, const FineWeights W, const double* b, double* x, double omega, stream_t st) {
     return pfor(g.size(), st, [=] SSRS_HD(i64 i) {
         if (g.excluded(i)) { x[i] = 0.0; return; }
         double ax, d;
-        fine_row<true, false>(g, i, b, ax, d);        // only the diagonal is used
+        fine_row_w<true>(g, W, i, b, ax, d);          // only the diagonal is used
         x[i] = omega * b[i] / d;
     });
 }
-inline int fine_jacobi(const FineGraph g, const double* b, const double* x, double* xn, double omega, stream_t st) {
+inline int fine_jacobi(const FineGraph g, const FineWeights W, const double* b, const double* x, double* xn, double omega, stream_t st) {
     return pfor(g.size(), st, [=] SSRS_HD(i64 i) {
         if (g.excluded(i)) { xn[i] = 0.0; return; }
         double ax, d;
-        fine_row<true, false>(g, i, x, ax, d);
+        fine_row_w<true>(g, W, i, x, ax, d);
         xn[i] = x[i] + omega * (b[i] - ax) / d;
     });
 }
 // residual per cell (coalesced) into `res`, then a deterministic per-aggregate sum
-inline int fine_restrict_residual(const FineGraph g, const Level& L, const double* b, const double* x, double* res,
-                                  double* bc, stream_t st) {
+inline int fine_restrict_residual(const FineGraph g, const FineWeights W, const Level& L, const double* b, const double* x,
+                                  double* res, double* bc, stream_t st) {
     if (pfor(g.size(), st, [=] SSRS_HD(i64 i) {
             if (g.excluded(i)) { res[i] = 0.0; return; }
             double ax, d;
-            fine_row<true, false>(g, i, x, ax, d);
+            fine_row_w<true>(g, W, i, x, ax, d);
             res[i] = b[i] - ax;
         }) != 0) return -1;
     const i64* memptr = L.memptr; const int* mem = L.mem;
@@ -542,11 +590,11 @@ inline int fine_restrict_residual(const FineGraph g, const Level& L, const doubl
         bc[I] = s;
     });
 }
-inline int fine_smooth(const FineGraph g, const double* b, double*& x, double*& t, int sweeps, bool zero_guess,
-                       double omega, stream_t st) {
+inline int fine_smooth(const FineGraph g, const FineWeights W, const double* b, double*& x, double*& t, int sweeps,
+                       bool zero_guess, double omega, stream_t st) {
     for (int s = 0; s < sweeps; ++s) {
-        if (s == 0 && zero_guess) { AMG_TRY(fine_jacobi_first(g, b, x, omega, st)); }
-        else { AMG_TRY(fine_jacobi(g, b, x, t, omega, st)); double* sw = x; x = t; t = sw; }
+        if (s == 0 && zero_guess) { AMG_TRY(fine_jacobi_first(g, W, b, x, omega, st)); }
+        else { AMG_TRY(fine_jacobi(g, W, b, x, t, omega, st)); double* sw = x; x = t; t = sw; }
     }
     return SSRS_OK;
 }
@@ -566,11 +614,11 @@ int coarse_solve(Hierarchy& H, Level& C, stream_t st) {
 int vcycle(Hierarchy& H, const double* rhs, double*& out, double*& tmp, stream_t st) {
     const int nl = (int)H.lv.size();
     if (nl == 1) {          // no coarse level: plain Jacobi sweeps
-        return fine_smooth(H.fine, rhs, out, tmp, 2 * H.nu, true, H.omega, st);
+        return fine_smooth(H.fine, H.fw, rhs, out, tmp, 2 * H.nu, true, H.omega, st);
     }
-    int rc = fine_smooth(H.fine, rhs, out, tmp, H.nu, true, H.omega, st);
+    int rc = fine_smooth(H.fine, H.fw, rhs, out, tmp, H.nu, true, H.omega, st);
     if (rc) return rc;
-    AMG_TRY(fine_restrict_residual(H.fine, H.lv[0], rhs, out, H.fres, H.lv[1].b, st));
+    AMG_TRY(fine_restrict_residual(H.fine, H.fw, H.lv[0], rhs, out, H.fres, H.lv[1].b, st));
     for (int l = 1; l < nl - 1; ++l) {
         Level& L = H.lv[l];
         rc = smooth(csr_of(L), L.b, L.x, L.t, H.nu, true, H.omega, st);
@@ -586,7 +634,7 @@ int vcycle(Hierarchy& H, const double* rhs, double*& out, double*& tmp, stream_t
         if (rc) return rc;
     }
     AMG_TRY(prolong_add(H.lv[0], H.fine.size(), out, H.lv[1].x, st));
-    return fine_smooth(H.fine, rhs, out, tmp, H.nu, false, H.omega, st);
+    return fine_smooth(H.fine, H.fw, rhs, out, tmp, H.nu, false, H.omega, st);
 }
 
 int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
@@ -618,21 +666,21 @@ int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
 }
 
 // out = b - A x at free nodes (b = 0 there: the Dirichlet values live in x), 0 at Dirichlet nodes; *nrm2 = |out|^2
-int fine_residual(const FineGraph fg, const double* x, double* out, double* nrm2, stream_t st) {
+int fine_residual(const FineGraph fg, const FineWeights W, const double* x, double* out, double* nrm2, stream_t st) {
     const i64 n = fg.size();
     AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
         if (fg.excluded(i)) { out[i] = 0.0; return; }
-        double ax, d; fine_row<false, true>(fg, i, x, ax, d);
+        double ax, d; fine_row_w<false>(fg, W, i, x, ax, d);
         out[i] = -ax;
     }));
     AMG_TRY(preduce_sum(n, st, nrm2, [=] SSRS_HD(i64 i) { return out[i] * out[i]; }));
     return SSRS_OK;
 }
 // out = A in for a correction vector `in` (zero at Dirichlet nodes)
-int fine_apply(const FineGraph fg, const double* in, double* out, stream_t st) {
+int fine_apply(const FineGraph fg, const FineWeights W, const double* in, double* out, stream_t st) {
     AMG_TRY(pfor(fg.size(), st, [=] SSRS_HD(i64 i) {
         if (fg.excluded(i)) { out[i] = 0.0; return; }
-        double ax, d; fine_row<false, false>(fg, i, in, ax, d);
+        double ax, d; fine_row_w<false>(fg, W, i, in, ax, d);
         out[i] = ax;
     }));
     return SSRS_OK;
@@ -708,6 +756,24 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     }
     H.fine.kd = kd; H.fine.rows = rows; H.fine.cols = cols; H.fine.interior_dirichlet = interior;
     AMG_ALLOC(H.fres, double, n);
+    {
+        float* wf; double* wd;
+        AMG_ALLOC(wf, float, 4 * n);
+        AMG_ALLOC(wd, double, 4 * n);
+        const FineGraph fgw = H.fine;
+        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+            const int r = (int)(i / cols), c = (int)(i - (i64)r * cols);
+            const float kc = fgw.kd[i];
+            const bool hasE = c < cols - 1, hasN = r < rows - 1, hasW = c > 0;
+            const double e = hasE ? link_weight<false>(kc, fgw.kd[i + 1], false) : 0.0;
+            const double nn = hasN ? link_weight<false>(kc, fgw.kd[i + cols], false) : 0.0;
+            const double ne = (hasN && hasE) ? link_weight<false>(kc, fgw.kd[i + cols + 1], true) : 0.0;
+            const double nw = (hasN && hasW) ? link_weight<false>(kc, fgw.kd[i + cols - 1], true) : 0.0;
+            wd[i] = e; wd[n + i] = nn; wd[2 * n + i] = ne; wd[3 * n + i] = nw;
+            wf[i] = (float)e; wf[n + i] = (float)nn; wf[2 * n + i] = (float)ne; wf[3 * n + i] = (float)nw;
+        }));
+        H.fw.wf = wf; H.fw.wd = wd;
+    }
 
     // ---- setup: hierarchy ----
     const double theta = 0.5;
@@ -743,7 +809,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     // ---- BiCGStab, right preconditioned ----
     const FineGraph fg = H.fine;
     double r0n2 = 0.0;
-    { int rc = fine_residual(fg, x, r, &r0n2, st); if (rc) return rc; }
+    { int rc = fine_residual(fg, H.fw, x, r, &r0n2, st); if (rc) return rc; }
     const double r0 = sqrt(r0n2);
     int iters = 0, restarts = 0, converged = (r0 == 0.0);
     double best_true = 1.0;
@@ -763,7 +829,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             { double *pp = p; const double *rr = r, *vv = v; const double om_ = om;
               AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) { pp[i] = rr[i] + beta * (pp[i] - om_ * vv[i]); })); }
             { int rc = vcycle(H, p, y, y2, st); if (rc) return rc; }
-            { int rc = fine_apply(fg, y, v, st); if (rc) return rc; }
+            { int rc = fine_apply(fg, H.fw, y, v, st); if (rc) return rc; }
             double rhv = 0.0;
             { const double *a_ = rh, *b_ = v; AMG_TRY(preduce_sum(n, st, &rhv, [=] SSRS_HD(i64 i) { return a_[i] * b_[i]; })); }
             if (rhv == 0.0) { breakdown = true; break; }
@@ -771,7 +837,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             { double* ss = s; const double *rr = r, *vv = v; const double al = alpha;
               AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) { ss[i] = rr[i] - al * vv[i]; })); }
             { int rc = vcycle(H, s, z, z2, st); if (rc) return rc; }
-            { int rc = fine_apply(fg, z, t, st); if (rc) return rc; }
+            { int rc = fine_apply(fg, H.fw, z, t, st); if (rc) return rc; }
             double ts = 0.0, tt = 0.0;
             { const double *a_ = t, *b_ = s;
               AMG_TRY(preduce_sum2(n, st, &ts, &tt, [=] SSRS_HD(i64 i, double& u0, double& u1) { u0 = a_[i] * b_[i]; u1 = a_[i] * a_[i]; })); }
@@ -791,7 +857,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         }
         // true residual: accept, or restart from the current iterate
         double tn2 = 0.0;
-        { int rc = fine_residual(fg, x, r, &tn2, st); if (rc) return rc; }
+        { int rc = fine_residual(fg, H.fw, x, r, &tn2, st); if (rc) return rc; }
         rel = sqrt(tn2) / r0;
         if (!(rel == rel)) { set_error("ssrs_potential_solve: NaN residual (NaN in the conductivity raster?)"); return SSRS_ERR_NOT_CONVERGED; }
         if (rel <= 4.0 * rtol) converged = 1;
