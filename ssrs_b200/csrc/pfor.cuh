@@ -27,8 +27,8 @@ namespace par {
 #define SSRS_HD
 typedef void* stream_t;
 
-inline int dev_alloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
-inline void dev_free(void* p) { free(p); }
+inline int dev_alloc(void** p, size_t bytes, stream_t) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
+inline void dev_free(void* p, stream_t) { free(p); }
 inline int dev_zero(void* p, size_t bytes, stream_t) { memset(p, 0, bytes); return 0; }
 inline int dev_fill_byte(void* p, int v, size_t bytes, stream_t) { memset(p, v, bytes); return 0; }
 inline int copy_d2d(void* d, const void* s, size_t bytes, stream_t) { memcpy(d, s, bytes); return 0; }
@@ -68,8 +68,10 @@ inline int atomic_add_int(int* p, int v) { int o = *p; *p = o + v; return o; }
 #define SSRS_HD __host__ __device__
 typedef cudaStream_t stream_t;
 
-inline int dev_alloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
-inline void dev_free(void* p) { if (p) cudaFree(p); }
+// stream-ordered allocation from the device's default memory pool: freed blocks stay cached in the pool
+// (release threshold raised in potential.cu), so repeated solves do not pay cudaMalloc/cudaFree
+inline int dev_alloc(void** p, size_t bytes, cudaStream_t s) { return cudaMallocAsync(p, bytes ? bytes : 1, s) == cudaSuccess ? 0 : -1; }
+inline void dev_free(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
 inline int dev_zero(void* p, size_t bytes, stream_t s) { return cudaMemsetAsync(p, 0, bytes, s) == cudaSuccess ? 0 : -1; }
 inline int dev_fill_byte(void* p, int v, size_t bytes, stream_t s) { return cudaMemsetAsync(p, v, bytes, s) == cudaSuccess ? 0 : -1; }
 inline int copy_d2d(void* d, const void* s, size_t b, stream_t st) { return cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : -1; }
@@ -160,11 +162,11 @@ inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t
     size_t tmp_bytes = 0;
     if (cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, data, data, n, s) != cudaSuccess) return -1;
     void* tmp = nullptr;
-    if (cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) return -1;
+    if (cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s) != cudaSuccess) return -1;
     cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, data, data, n, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_out, data + n - 1, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, s);
     if (e != cudaSuccess) return -1;
     *total = last_in + last_out;
     return 0;

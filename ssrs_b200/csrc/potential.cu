@@ -43,7 +43,7 @@ void set_error(const char* fmt, ...) {
 int sm_count();
 namespace par {
 int grid_cap() { return sm_count() * 8; }
-double* reduce_scratch() {
+double* reduce_scratch() {   // small persistent buffer (plain cudaMalloc, lives for the process)
     static thread_local double* buf = nullptr;
     static thread_local int dev_of = -1;
     int dev = 0;
@@ -273,18 +273,20 @@ SSRS_HD inline void fine_row_w(const FineGraph& g, const FineWeights& W, i64 i, 
 struct Pool {
     std::vector<void*> ptrs;
     size_t bytes = 0;
+    stream_t st;
+    explicit Pool(stream_t s) : st(s) {}
     template <class T> T* get(i64 count) {
         void* p = nullptr;
-        if (dev_alloc(&p, sizeof(T) * (size_t)(count > 0 ? count : 1)) != 0) return nullptr;
+        if (dev_alloc(&p, sizeof(T) * (size_t)(count > 0 ? count : 1), st) != 0) return nullptr;
         ptrs.push_back(p);
         bytes += sizeof(T) * (size_t)count;
         return static_cast<T*>(p);
     }
     void release(void* p) {
         for (size_t k = 0; k < ptrs.size(); ++k)
-            if (ptrs[k] == p) { dev_free(p); ptrs.erase(ptrs.begin() + k); return; }
+            if (ptrs[k] == p) { dev_free(p, st); ptrs.erase(ptrs.begin() + k); return; }
     }
-    ~Pool() { for (void* p : ptrs) dev_free(p); }
+    ~Pool() { for (void* p : ptrs) dev_free(p, st); }
 };
 
 struct Level {
@@ -302,7 +304,7 @@ template <class G>
 int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_rounds, stream_t st) {
     const i64 n = g.size();
     float* rowmax; int *mate, *best, *root, *root2;
-    Pool tmp;
+    Pool tmp(st);
     rowmax = tmp.get<float>(n); mate = tmp.get<int>(n); best = tmp.get<int>(n); root = tmp.get<int>(n); root2 = tmp.get<int>(n);
     if (!rowmax || !mate || !best || !root || !root2) { set_error("ssrs_potential_solve: out of device memory in coarsen"); return SSRS_ERR_CUDA; }
     const float th = (float)theta;
@@ -424,7 +426,7 @@ template <class G>
 int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
     const i64 nc = L.nc;
     const int* agg = L.agg; const i64* memptr = L.memptr; const int* mem = L.mem;
-    Pool tmp;
+    Pool tmp(st);
     i64* off = tmp.get<i64>(nc + 1);
     int* len = tmp.get<int>(nc);
     if (!off || !len) { set_error("ssrs_potential_solve: out of device memory in galerkin"); return SSRS_ERR_CUDA; }
@@ -640,7 +642,7 @@ int vcycle(Hierarchy& H, const double* rhs, double*& out, double*& tmp, stream_t
 int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
     const i64 n = C.n;
     double *D, *I, *colk, *rowD, *rowI;
-    Pool tmp;
+    Pool tmp(st);
     D = tmp.get<double>(n * n); colk = tmp.get<double>(n); rowD = tmp.get<double>(n); rowI = tmp.get<double>(n);
     AMG_ALLOC(I, double, n * n);
     if (!D || !colk || !rowD || !rowI) { set_error("ssrs_potential_solve: out of device memory in dense_inverse"); return SSRS_ERR_CUDA; }
@@ -715,7 +717,16 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     stream_t st = (stream_t)stream;
     const i64 n = (i64)rows * cols;
     const double t_begin = now_ms();
-    Pool pool;
+#ifndef SSRS_HOST_EMU
+    {   // keep freed workspace cached in the device's default pool between solves
+        int dev = 0; cudaMemPool_t mp;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+            uint64_t thresh = ~0ULL;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thresh);
+        }
+    }
+#endif
+    Pool pool(st);
     Hierarchy H;
 
     // Dirichlet nodes arrive as the reference's column-major ids (movmodel.py:25-29): i = col*nrow + row
