@@ -55,6 +55,20 @@ inline int preduce_sum2(int64_t n, stream_t, double* out0, double* out1, F f) {
     *out0 = s0; *out1 = s1;
     return 0;
 }
+template <class F>
+inline int pfor2d(int rows, int cols, stream_t, F f) {
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) f(r, c);
+    return 0;
+}
+template <class F>
+inline int preduce2d_sum2(int rows, int cols, stream_t, double* out0, double* out1, F f) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) { double a, b; f(r, c, a, b); s0 += a; s1 += b; }
+    *out0 = s0; *out1 = s1;
+    return 0;
+}
 inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t) {
     int64_t run = 0;
     for (int64_t i = 0; i < n; ++i) { int64_t v = data[i]; data[i] = run; run += v; }
@@ -92,6 +106,21 @@ inline int pfor(int64_t n, stream_t s, F f) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > grid_cap()) blocks = grid_cap();
     pfor_kernel<<<(int)blocks, 256, 0, s>>>(n, f);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// raster kernels: one thread per cell, 32 x 8 cells per CTA; f(row, col)
+template <class F>
+__global__ void __launch_bounds__(256) pfor2d_kernel(int rows, int cols, F f) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r = blockIdx.y * 8 + threadIdx.y;
+    if (r < rows && c < cols) f(r, c);
+}
+template <class F>
+inline int pfor2d(int rows, int cols, stream_t s, F f) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 7) / 8));
+    pfor2d_kernel<<<grid, dim3(32, 8), 0, s>>>(rows, cols, f);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -138,6 +167,40 @@ inline int preduce_sum2(int64_t n, stream_t s, double* out0, double* out1, F f) 
     if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
     if (blocks < 1) blocks = 1;
     reduce2_kernel<<<(int)blocks, 256, 0, s>>>(n, scratch, f);
+    reduce_final_kernel<<<1, 256, 0, s>>>(scratch, (int)blocks, scratch + 2 * RED_BLOCKS);
+    double h[2];
+    if (cudaMemcpyAsync(h, scratch + 2 * RED_BLOCKS, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+    *out0 = h[0]; *out1 = h[1];
+    return 0;
+}
+// the same over a raster: CTAs stride over 32 x 8 tiles in a fixed order
+template <class F>
+__global__ void __launch_bounds__(256) reduce2d_kernel(int rows, int cols, int tiles_x, int64_t tiles, double* partial, F f) {
+    double s0 = 0.0, s1 = 0.0;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int by = (int)(t / tiles_x), bx = (int)(t - (int64_t)by * tiles_x);
+        const int r = by * 8 + ty, c = bx * 32 + tx;
+        if (r < rows && c < cols) {
+            double a, b;
+            f(r, c, a, b);
+            s0 += a; s1 += b;
+        }
+    }
+    s0 = block_sum(s0);
+    s1 = block_sum(s1);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s0; partial[RED_BLOCKS + blockIdx.x] = s1; }
+}
+template <class F>
+inline int preduce2d_sum2(int rows, int cols, stream_t s, double* out0, double* out1, F f) {
+    double* scratch = reduce_scratch();
+    if (!scratch) return -1;
+    const int tiles_x = (cols + 31) / 32;
+    const int64_t tiles = (int64_t)tiles_x * ((rows + 7) / 8);
+    int64_t blocks = tiles < RED_BLOCKS ? tiles : RED_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    reduce2d_kernel<<<(int)blocks, 256, 0, s>>>(rows, cols, tiles_x, tiles, scratch, f);
     reduce_final_kernel<<<1, 256, 0, s>>>(scratch, (int)blocks, scratch + 2 * RED_BLOCKS);
     double h[2];
     if (cudaMemcpyAsync(h, scratch + 2 * RED_BLOCKS, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
