@@ -76,7 +76,8 @@ SSRS_API int ssrs_threshold(const float* in, float* out, int64_t n, float thresh
  * conductivity: float32 [rows][cols] thresholded updraft (the `conductivity` argument of the reference).
  * bnodes_host / bvalues_host: HOST arrays exactly as MovModel.get_boundary_nodes() returns them
  *   (ssrs/movmodel.py:21-57): column-major node ids `col*rows + row` and their Dirichlet values.
- * rtol: relative 2-norm residual of the un-normalised system (<= 0 -> 1e-9); max_iter <= 0 -> 300.
+ * rtol: relative 2-norm residual of the un-normalised system; <= 0 (default) iterates to the accuracy float64 can
+ *   attain (the solver estimates the residual floor d_i*ulp(phi_i)/2 and stops within it); max_iter <= 0 -> 300.
  * potential: float32 [rows][cols] out (the reference returns float32, :128).
  * Allocates its workspace internally (cudaMalloc) and frees it before returning; synchronous.
  * Returns SSRS_ERR_NOT_CONVERGED (potential still written) if the tolerance was not reached.
@@ -98,6 +99,52 @@ SSRS_API int ssrs_potential_solve(const float* conductivity, int rows, int cols,
                                   const int64_t* bnodes_host, const double* bvalues_host, int64_t n_bnodes,
                                   double rtol, int max_iter, float* potential, ssrs_solve_stats* stats,
                                   void* stream);
+
+/* Row-sharded solve (BASELINE config 5): the grid's rows are split into `comm->size` contiguous
+ * slabs; rank r owns slab r.  Every rank passes the SAME full conductivity raster (fields are replicated for the
+ * stepping stage anyway) and receives the full potential.  The hierarchy is built redundantly on every rank
+ * (identical, no communication; aggregates never straddle a slab boundary); the solve phase — V-cycles, operator
+ * applications, Krylov vectors — runs on the owned slab only and exchanges one-row halos (fine level) or the few
+ * boundary-adjacent entries (coarse levels) with the two neighbouring ranks before each operator application,
+ * plus one scalar all-reduce per inner product.  Levels below ~64 k rows are computed redundantly.
+ *
+ * ssrs_comm is the transport: plain function pointers, so the product uses NCCL over NVLink
+ * (ssrs_comm_create_nccl) and the CPU test build drives the same solver code over gloo.
+ * All three callbacks return 0 on success.  Offsets and sizes are in bytes. */
+typedef struct ssrs_comm {
+    int32_t rank, size;
+    void* ctx;
+    /* exchange contiguous ranges of ONE buffer with rank-1 ("up") and rank+1 ("down"); a size of 0 skips that
+     * transfer; stream-ordered */
+    int (*exchange)(void* ctx, void* base,
+                    int64_t send_up_off, int64_t send_up_bytes, int64_t recv_up_off, int64_t recv_up_bytes,
+                    int64_t send_dn_off, int64_t send_dn_bytes, int64_t recv_dn_off, int64_t recv_dn_bytes,
+                    void* stream);
+    /* in-place sum of `count` HOST doubles over all ranks; blocking; bit-identical result on every rank */
+    int (*allreduce_sum)(void* ctx, double* values_host, int32_t count, void* stream);
+    /* in-place all-gather: rank r contributes bytes [offsets_host[r], offsets_host[r+1]) of `base` */
+    int (*allgather)(void* ctx, void* base, const int64_t* offsets_host, void* stream);
+    /* in-place sum of a device uint32 array over all ranks (presence maps); stream-ordered */
+    int (*allreduce_u32)(void* ctx, uint32_t* values, int64_t count, void* stream);
+} ssrs_comm;
+
+#define SSRS_MAX_RANKS 16
+
+SSRS_API int ssrs_potential_solve_sharded(const float* conductivity, int rows, int cols,
+                                          const int64_t* bnodes_host, const double* bvalues_host, int64_t n_bnodes,
+                                          double rtol, int max_iter, float* potential, ssrs_solve_stats* stats,
+                                          const ssrs_comm* comm, void* stream);
+
+/* NCCL transport (one process per GPU).  Rank 0 calls ssrs_nccl_unique_id and distributes the 128 bytes by any
+ * means (the Python host uses torch.distributed); every rank then calls ssrs_comm_create_nccl collectively. */
+SSRS_API int ssrs_nccl_unique_id(void* id128_host);
+SSRS_API int ssrs_comm_create_nccl(const void* id128_host, int rank, int size, ssrs_comm** comm_out);
+SSRS_API int ssrs_comm_destroy(ssrs_comm* comm);
+
+/* Presence-map reduction over the ranks that stepped disjoint blocks of tracks: in-place
+ * sum of the uint32 count raster, one collective per (case, realisation) map.  Counts are integers, so the
+ * result is independent of the number of ranks. */
+SSRS_API int ssrs_presence_allreduce(uint32_t* presence, int64_t n, const ssrs_comm* comm, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 3+4 — batched track stepping with fused presence accumulation.  Replaces

@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed for {cmd[-3]}")
     if force or jobs or _stale(LIB, objs):
         cmd = [nvcc(), *ARCH, "-shared", "-cudart", "shared", "-o", LIB, *objs,
-               "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
+               "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -37,34 +37,27 @@ inline int copy_d2h(void* d, const void* s, size_t bytes, stream_t) { memcpy(d, 
 inline int sync(stream_t) { return 0; }
 
 template <class F>
-inline int pfor(int64_t n, stream_t, F f) {
-    for (int64_t i = 0; i < n; ++i) f(i);
+inline int pfor_range(int64_t i0, int64_t i1, stream_t, F f) {
+    for (int64_t i = i0; i < i1; ++i) f(i);
     return 0;
 }
 template <class F>
-inline int preduce_sum(int64_t n, stream_t, double* out, F f) {
-    double s = 0.0;
-    for (int64_t i = 0; i < n; ++i) s += f(i);
-    *out = s;
-    return 0;
-}
-template <class F>
-inline int preduce_sum2(int64_t n, stream_t, double* out0, double* out1, F f) {
+inline int preduce_sum2_range(int64_t i0, int64_t i1, stream_t, double* out0, double* out1, F f) {
     double s0 = 0.0, s1 = 0.0;
-    for (int64_t i = 0; i < n; ++i) { double a, b; f(i, a, b); s0 += a; s1 += b; }
+    for (int64_t i = i0; i < i1; ++i) { double a, b; f(i, a, b); s0 += a; s1 += b; }
     *out0 = s0; *out1 = s1;
     return 0;
 }
 template <class F>
-inline int pfor2d(int rows, int cols, stream_t, F f) {
-    for (int r = 0; r < rows; ++r)
+inline int pfor2d_rows(int r0, int r1, int cols, stream_t, F f) {
+    for (int r = r0; r < r1; ++r)
         for (int c = 0; c < cols; ++c) f(r, c);
     return 0;
 }
 template <class F>
-inline int preduce2d_sum2(int rows, int cols, stream_t, double* out0, double* out1, F f) {
+inline int preduce2d_sum2_rows(int r0, int r1, int cols, stream_t, double* out0, double* out1, F f) {
     double s0 = 0.0, s1 = 0.0;
-    for (int r = 0; r < rows; ++r)
+    for (int r = r0; r < r1; ++r)
         for (int c = 0; c < cols; ++c) { double a, b; f(r, c, a, b); s0 += a; s1 += b; }
     *out0 = s0; *out1 = s1;
     return 0;
@@ -76,6 +69,8 @@ inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t
     return 0;
 }
 inline int atomic_add_int(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline void atomic_min_i64(int64_t* p, int64_t v) { if (v < *p) *p = v; }
+inline void atomic_max_i64(int64_t* p, int64_t v) { if (v > *p) *p = v; }
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -96,31 +91,32 @@ inline int sync(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0
 int grid_cap();     // SM count x 8 (defined in potential.cu)
 
 template <class F>
-__global__ void __launch_bounds__(256) pfor_kernel(int64_t n, F f) {
+__global__ void __launch_bounds__(256) pfor_kernel(int64_t i0, int64_t i1, F f) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) f(i);
 }
 template <class F>
-inline int pfor(int64_t n, stream_t s, F f) {
+inline int pfor_range(int64_t i0, int64_t i1, stream_t s, F f) {
+    const int64_t n = i1 - i0;
     if (n <= 0) return 0;
     int64_t blocks = (n + 255) / 256;
     if (blocks > grid_cap()) blocks = grid_cap();
-    pfor_kernel<<<(int)blocks, 256, 0, s>>>(n, f);
+    pfor_kernel<<<(int)blocks, 256, 0, s>>>(i0, i1, f);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // raster kernels: one thread per cell, 32 x 8 cells per CTA; f(row, col)
 template <class F>
-__global__ void __launch_bounds__(256) pfor2d_kernel(int rows, int cols, F f) {
+__global__ void __launch_bounds__(256) pfor2d_kernel(int r0, int r1, int cols, F f) {
     const int c = blockIdx.x * 32 + threadIdx.x;
-    const int r = blockIdx.y * 8 + threadIdx.y;
-    if (r < rows && c < cols) f(r, c);
+    const int r = r0 + blockIdx.y * 8 + threadIdx.y;
+    if (r < r1 && c < cols) f(r, c);
 }
 template <class F>
-inline int pfor2d(int rows, int cols, stream_t s, F f) {
-    if (rows <= 0 || cols <= 0) return 0;
-    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 7) / 8));
-    pfor2d_kernel<<<grid, dim3(32, 8), 0, s>>>(rows, cols, f);
+inline int pfor2d_rows(int r0, int r1, int cols, stream_t s, F f) {
+    if (r1 <= r0 || cols <= 0) return 0;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((r1 - r0 + 7) / 8));
+    pfor2d_kernel<<<grid, dim3(32, 8), 0, s>>>(r0, r1, cols, f);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -139,10 +135,10 @@ __device__ __forceinline__ double block_sum(double v) {
     return t;   // valid in thread 0
 }
 template <class F>
-__global__ void __launch_bounds__(256) reduce2_kernel(int64_t n, double* partial, F f) {
+__global__ void __launch_bounds__(256) reduce2_kernel(int64_t i0, int64_t i1, double* partial, F f) {
     double s0 = 0.0, s1 = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
         double a, b;
         f(i, a, b);
         s0 += a; s1 += b;
@@ -160,13 +156,13 @@ __global__ void __launch_bounds__(256) reduce_final_kernel(const double* partial
 }
 // Deterministic two-stage reductions (fixed grid, fixed tree); the result is read back (stream sync).
 template <class F>
-inline int preduce_sum2(int64_t n, stream_t s, double* out0, double* out1, F f) {
+inline int preduce_sum2_range(int64_t i0, int64_t i1, stream_t s, double* out0, double* out1, F f) {
     double* scratch = reduce_scratch();
     if (!scratch) return -1;
-    int64_t blocks = (n + 255) / 256;
+    int64_t blocks = (i1 - i0 + 255) / 256;
     if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
     if (blocks < 1) blocks = 1;
-    reduce2_kernel<<<(int)blocks, 256, 0, s>>>(n, scratch, f);
+    reduce2_kernel<<<(int)blocks, 256, 0, s>>>(i0, i1, scratch, f);
     reduce_final_kernel<<<1, 256, 0, s>>>(scratch, (int)blocks, scratch + 2 * RED_BLOCKS);
     double h[2];
     if (cudaMemcpyAsync(h, scratch + 2 * RED_BLOCKS, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
@@ -176,12 +172,12 @@ inline int preduce_sum2(int64_t n, stream_t s, double* out0, double* out1, F f) 
 }
 // the same over a raster: CTAs stride over 32 x 8 tiles in a fixed order
 template <class F>
-__global__ void __launch_bounds__(256) reduce2d_kernel(int rows, int cols, int tiles_x, int64_t tiles, double* partial, F f) {
+__global__ void __launch_bounds__(256) reduce2d_kernel(int r0, int rows, int cols, int tiles_x, int64_t tiles, double* partial, F f) {
     double s0 = 0.0, s1 = 0.0;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int by = (int)(t / tiles_x), bx = (int)(t - (int64_t)by * tiles_x);
-        const int r = by * 8 + ty, c = bx * 32 + tx;
+        const int r = r0 + by * 8 + ty, c = bx * 32 + tx;
         if (r < rows && c < cols) {
             double a, b;
             f(r, c, a, b);
@@ -193,30 +189,20 @@ __global__ void __launch_bounds__(256) reduce2d_kernel(int rows, int cols, int t
     if (threadIdx.x == 0) { partial[blockIdx.x] = s0; partial[RED_BLOCKS + blockIdx.x] = s1; }
 }
 template <class F>
-inline int preduce2d_sum2(int rows, int cols, stream_t s, double* out0, double* out1, F f) {
+inline int preduce2d_sum2_rows(int r0, int r1, int cols, stream_t s, double* out0, double* out1, F f) {
     double* scratch = reduce_scratch();
     if (!scratch) return -1;
     const int tiles_x = (cols + 31) / 32;
-    const int64_t tiles = (int64_t)tiles_x * ((rows + 7) / 8);
+    const int64_t tiles = (int64_t)tiles_x * ((r1 - r0 + 7) / 8);
     int64_t blocks = tiles < RED_BLOCKS ? tiles : RED_BLOCKS;
     if (blocks < 1) blocks = 1;
-    reduce2d_kernel<<<(int)blocks, 256, 0, s>>>(rows, cols, tiles_x, tiles, scratch, f);
+    reduce2d_kernel<<<(int)blocks, 256, 0, s>>>(r0, r1, cols, tiles_x, tiles, scratch, f);
     reduce_final_kernel<<<1, 256, 0, s>>>(scratch, (int)blocks, scratch + 2 * RED_BLOCKS);
     double h[2];
     if (cudaMemcpyAsync(h, scratch + 2 * RED_BLOCKS, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
     *out0 = h[0]; *out1 = h[1];
     return 0;
-}
-template <class F>
-struct OneOfTwo {
-    F f;
-    __host__ __device__ void operator()(int64_t i, double& a, double& b) const { a = f(i); b = 0.0; }
-};
-template <class F>
-inline int preduce_sum(int64_t n, stream_t s, double* out, F f) {
-    double dummy;
-    return preduce_sum2(n, s, out, &dummy, OneOfTwo<F>{f});
 }
 inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t s) {
     if (n <= 0) { *total = 0; return 0; }
@@ -241,7 +227,38 @@ __host__ __device__ __forceinline__ int atomic_add_int(int* p, int v) {
     int o = *p; *p = o + v; return o;
 #endif
 }
+__host__ __device__ __forceinline__ void atomic_min_i64(int64_t* p, int64_t v) {
+#ifdef __CUDA_ARCH__
+    atomicMin((long long*)p, (long long)v);
+#else
+    if (v < *p) *p = v;
 #endif
+}
+__host__ __device__ __forceinline__ void atomic_max_i64(int64_t* p, int64_t v) {
+#ifdef __CUDA_ARCH__
+    atomicMax((long long*)p, (long long)v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+#endif
+
+// whole-range forms
+template <class F> inline int pfor(int64_t n, stream_t s, F f) { return pfor_range(0, n, s, f); }
+template <class F> inline int pfor2d(int rows, int cols, stream_t s, F f) { return pfor2d_rows(0, rows, cols, s, f); }
+template <class F> inline int preduce_sum2(int64_t n, stream_t s, double* o0, double* o1, F f) { return preduce_sum2_range(0, n, s, o0, o1, f); }
+template <class F> inline int preduce2d_sum2(int rows, int cols, stream_t s, double* o0, double* o1, F f) { return preduce2d_sum2_rows(0, rows, cols, s, o0, o1, f); }
+template <class F>
+struct OneOfTwoR {
+    F f;
+    SSRS_HD void operator()(int64_t i, double& a, double& b) const { a = f(i); b = 0.0; }
+};
+template <class F>
+inline int preduce_sum_range(int64_t i0, int64_t i1, stream_t s, double* out, F f) {
+    double dummy;
+    return preduce_sum2_range(i0, i1, s, out, &dummy, OneOfTwoR<F>{f});
+}
+template <class F> inline int preduce_sum(int64_t n, stream_t s, double* out, F f) { return preduce_sum_range(0, n, s, out, f); }
 
 }  // namespace par
 }  // namespace ssrs

@@ -84,12 +84,31 @@ SSRS_HD inline unsigned pair_hash(unsigned a, unsigned b) {
     return h;
 }
 
+// ---- ownership of a level's nodes (row-sharded solve) ------------------------------------------------------
+// part p owns the contiguous index range [lo[p], lo[p+1]); n == 1 is the single-GPU case
+struct Parts {
+    int n = 1;
+    i64 lo[SSRS_MAX_RANKS + 1] = {0};
+};
+SSRS_HD inline bool parts_cross(const Parts& P, i64 i, i64 j) {
+    for (int p = 1; p < P.n; ++p)
+        if ((i < P.lo[p]) != (j < P.lo[p])) return true;
+    return false;
+}
+SSRS_HD inline int parts_owner(const Parts& P, i64 i) {
+    int p = 0;
+    while (p + 1 < P.n && i >= P.lo[p + 1]) ++p;
+    return p;
+}
+
 // ---- graph providers ----------------------------------------------------------------------------
 // entry(i, k, j, a): k-th stored entry of row i -> kind, column j, value a (off-diagonals are negative).
 struct FineGraph {
     const float* kd;     // conductivity with the sign bit marking Dirichlet nodes
     int rows, cols;
     int interior_dirichlet;   // 1 if some Dirichlet node is more than one cell away from the border
+    Parts parts;
+    SSRS_HD bool crosses(i64 i, i64 j) const { return parts_cross(parts, i, j); }
     SSRS_HD i64 size() const { return (i64)rows * cols; }
     SSRS_HD bool excluded(i64 i) const { return sign_set(kd[i]); }
     SSRS_HD void range(i64, i64& k0, i64& k1) const { k0 = 0; k1 = 9; }
@@ -118,6 +137,8 @@ struct CsrGraph {
     const int* col;
     const double* val;
     i64 n;
+    Parts parts;
+    SSRS_HD bool crosses(i64 i, i64 j) const { return parts_cross(parts, i, j); }
     SSRS_HD i64 size() const { return n; }
     SSRS_HD bool excluded(i64) const { return false; }
     SSRS_HD void range(i64 i, i64& k0, i64& k1) const { k0 = rowptr[i]; k1 = rowptr[i + 1]; }
@@ -214,6 +235,9 @@ struct Level {
     i64* sptr = nullptr; int* ecol = nullptr; float* eval = nullptr; i64 ell_entries = 0;   // sliced ELL, float32 (levels >= 1)
     real *excess = nullptr, *dinv = nullptr;
     real *x32 = nullptr, *b32 = nullptr, *t32 = nullptr, *r32 = nullptr;      // cycle vectors (levels >= 1)
+    // row-sharded solve: ownership of this level's nodes and, per part, the index range its rows reference
+    Parts parts;
+    i64 ref_lo[SSRS_MAX_RANKS] = {0}, ref_hi[SSRS_MAX_RANKS] = {0};             // [ref_lo, ref_hi) incl. the own range
 };
 
 #define AMG_TRY(expr) do { if ((expr) != 0) { set_error("ssrs_potential_solve: device operation failed: %s", #expr); return SSRS_ERR_CUDA; } } while (0)
@@ -221,7 +245,7 @@ struct Level {
 
 // ---- coarsening: pairwise matching + joins ---------------------------------------------------------
 template <class G>
-int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_rounds, stream_t st) {
+int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_rounds, Parts* next, stream_t st) {
     const i64 n = g.size();
     float* rowmax; int *mate, *best, *root, *root2;
     Pool tmp(st);
@@ -248,7 +272,7 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
                     i64 j; double a;
                     if (g.entry(i, k, j, a) != E_OFF) continue;
                     const float w = (float)(-a);
-                    if (!(w > 0.0f) || mate[j] != -1) continue;
+                    if (!(w > 0.0f) || mate[j] != -1 || g.crosses(i, j)) continue;   // aggregates never straddle a slab boundary
                     const float rmj = rowmax[j];
                     if (w < th * (rmi > rmj ? rmi : rmj)) continue;           // strong from both sides
                     const unsigned h = pair_hash((unsigned)i, (unsigned)j);
@@ -277,7 +301,7 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
                     i64 j; double a;
                     if (g.entry(i, k, j, a) != E_OFF) continue;
                     const float w = (float)(-a);
-                    if (!(w > 0.0f) || root[j] < 0 || w < th * rmi) continue;  // strong for i, target already aggregated
+                    if (!(w > 0.0f) || root[j] < 0 || w < th * rmi || g.crosses(i, j)) continue;  // strong for i, target already aggregated
                     const int two = (w >= th * rowmax[j]) ? 1 : 0;
                     const unsigned h = pair_hash((unsigned)i, (unsigned)j);
                     if (bj < 0 || two > btwo || (two == btwo && (w > bw || (w == bw && (h > bh || (h == bh && (int)j > bj)))))) {
@@ -302,6 +326,14 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
     }
     i64 nc = 0;
     AMG_TRY(exclusive_scan_i64(flag, n, &nc, st));
+    // ownership of the coarse nodes: numbering follows the roots, so every part's aggregates are contiguous
+    next->n = g.parts.n;
+    next->lo[0] = 0;
+    next->lo[next->n] = nc;
+    for (int p = 1; p < g.parts.n; ++p) {
+        if (g.parts.lo[p] >= n) next->lo[p] = nc;
+        else AMG_TRY(copy_d2h(&next->lo[p], flag + g.parts.lo[p], sizeof(i64), st));
+    }
     AMG_ALLOC(L.agg, int, n);
     AMG_ALLOC(L.memptr, i64, nc + 1);
     AMG_ALLOC(L.mem, int, n);
@@ -454,15 +486,17 @@ struct VecF { const real* p; SSRS_HD real operator()(i64 j) const { return p[j];
 struct FirstSweepFine { const double* b; const real* dinv; real omega; SSRS_HD real operator()(i64 j) const { return omega * dinv[j] * (real)b[j]; } };
 struct FirstSweepF { const real* b; const real* dinv; real omega; SSRS_HD real operator()(i64 j) const { return omega * dinv[j] * b[j]; } };
 
-inline int fine_first32(const Fine32 F, const double* b, real* x, real omega, stream_t st) {
-    return pfor2d(F.rows, F.cols, st, [=] SSRS_HD(int r, int c) {
+// All cycle kernels take the range they compute ([r0, r1) rows of the fine grid, [i0, i1) nodes of a coarse
+// level): the whole level on one GPU, the owned slab in the row-sharded solve.
+inline int fine_first32(const Fine32 F, int r0, int r1, const double* b, real* x, real omega, stream_t st) {
+    return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
         x[i] = omega * F.dinv[i] * (real)b[i];
     });
 }
 // x = first sweep, res = b - A x in one pass over b
-inline int fine_first_residual32(const Fine32 F, const double* b, real* x, real* res, real omega, stream_t st) {
-    return pfor2d(F.rows, F.cols, st, [=] SSRS_HD(int r, int c) {
+inline int fine_first_residual32(const Fine32 F, int r0, int r1, const double* b, real* x, real* res, real omega, stream_t st) {
+    return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
         if (F.dinv[i] == (real)0.0) { x[i] = (real)0.0; res[i] = (real)0.0; return; }
         const FirstSweepFine x1 = {b, F.dinv, omega};
@@ -470,16 +504,16 @@ inline int fine_first_residual32(const Fine32 F, const double* b, real* x, real*
         res[i] = (real)b[i] - fine_apply32(F, r, c, x1);
     });
 }
-inline int fine_residual32(const Fine32 F, const double* b, const real* x, real* res, stream_t st) {
-    return pfor2d(F.rows, F.cols, st, [=] SSRS_HD(int r, int c) {
+inline int fine_residual32(const Fine32 F, int r0, int r1, const double* b, const real* x, real* res, stream_t st) {
+    return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
         if (F.dinv[i] == (real)0.0) { res[i] = (real)0.0; return; }
         res[i] = (real)b[i] - fine_apply32(F, r, c, VecF{x});
     });
 }
 template <class OutT>
-inline int fine_jacobi32(const Fine32 F, const double* b, const real* x, OutT* xn, real omega, stream_t st) {
-    return pfor2d(F.rows, F.cols, st, [=] SSRS_HD(int r, int c) {
+inline int fine_jacobi32(const Fine32 F, int r0, int r1, const double* b, const real* x, OutT* xn, real omega, stream_t st) {
+    return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
         const real di = F.dinv[i];
         if (di == (real)0.0) { xn[i] = (OutT)0; return; }
@@ -506,34 +540,34 @@ SSRS_HD inline real ell_apply(const Ell& e, i64 i, const X& x) {
     for (i64 p = e.sptr[s] + (i & 31); p < p1; p += 32) acc += e.val[p] * (x(e.col[p]) - xi);
     return e.excess[i] * xi + acc;
 }
-inline int ell_first32(const Ell e, const real* b, real* x, real omega, stream_t st) {
-    return pfor(e.n, st, [=] SSRS_HD(i64 i) { x[i] = omega * e.dinv[i] * b[i]; });
+inline int ell_first32(const Ell e, i64 i0, i64 i1, const real* b, real* x, real omega, stream_t st) {
+    return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { x[i] = omega * e.dinv[i] * b[i]; });
 }
-inline int ell_first_residual32(const Ell e, const real* b, real* x, real* res, real omega, stream_t st) {
-    return pfor(e.n, st, [=] SSRS_HD(i64 i) {
+inline int ell_first_residual32(const Ell e, i64 i0, i64 i1, const real* b, real* x, real* res, real omega, stream_t st) {
+    return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
         const FirstSweepF x1 = {b, e.dinv, omega};
         x[i] = x1(i);
         res[i] = b[i] - ell_apply(e, i, x1);
     });
 }
-inline int ell_residual32(const Ell e, const real* b, const real* x, real* res, stream_t st) {
-    return pfor(e.n, st, [=] SSRS_HD(i64 i) { res[i] = b[i] - ell_apply(e, i, VecF{x}); });
+inline int ell_residual32(const Ell e, i64 i0, i64 i1, const real* b, const real* x, real* res, stream_t st) {
+    return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { res[i] = b[i] - ell_apply(e, i, VecF{x}); });
 }
-inline int ell_jacobi32(const Ell e, const real* b, const real* x, real* xn, real omega, stream_t st) {
-    return pfor(e.n, st, [=] SSRS_HD(i64 i) { xn[i] = x[i] + omega * e.dinv[i] * (b[i] - ell_apply(e, i, VecF{x})); });
+inline int ell_jacobi32(const Ell e, i64 i0, i64 i1, const real* b, const real* x, real* xn, real omega, stream_t st) {
+    return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { xn[i] = x[i] + omega * e.dinv[i] * (b[i] - ell_apply(e, i, VecF{x})); });
 }
-// bc_I = sum of the residual over the members of aggregate I (members ascending: deterministic)
-inline int restrict32(const Level& L, const real* res, real* bc, stream_t st) {
+// bc_I = sum of the residual over the members of aggregate I (members ascending: deterministic), I in [I0, I1)
+inline int restrict32(const Level& L, i64 I0, i64 I1, const real* res, real* bc, stream_t st) {
     const i64* memptr = L.memptr; const int* mem = L.mem;
-    return pfor(L.nc, st, [=] SSRS_HD(i64 I) {
+    return pfor_range(I0, I1, st, [=] SSRS_HD(i64 I) {
         real s = (real)0.0;
         for (i64 p = memptr[I]; p < memptr[I + 1]; ++p) s += res[mem[p]];
         bc[I] = s;
     });
 }
-inline int prolong_add32(const Level& L, i64 n, real* x, const real* xc, real scale, stream_t st) {
+inline int prolong_add32(const Level& L, i64 i0, i64 i1, real* x, const real* xc, real scale, stream_t st) {
     const int* agg = L.agg;
-    return pfor(n, st, [=] SSRS_HD(i64 i) { const int c = agg[i]; if (c >= 0) x[i] += scale * xc[c]; });
+    return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { const int c = agg[i]; if (c >= 0) x[i] += scale * xc[c]; });
 }
 
 struct Hierarchy {
@@ -548,10 +582,45 @@ struct Hierarchy {
     FineWeights fw = {nullptr, nullptr};
     Fine32 f32;
     real *xf = nullptr, *tf = nullptr, *resf = nullptr;   // fine-level cycle vectors
+    // row-sharded solve (comm == nullptr: one GPU, every range is the whole level)
+    const ssrs_comm* comm = nullptr;
+    int rank = 0, nparts = 1;
+    int lrep = 1 << 30;        // levels >= lrep are computed redundantly by every rank
+    stream_t st = nullptr;
 };
 
-inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; return g; }
+inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; g.parts = L.parts; return g; }
 inline Ell ell_of(const Level& L) { Ell e; e.sptr = L.sptr; e.col = L.ecol; e.val = L.eval; e.excess = L.excess; e.dinv = L.dinv; e.n = L.n; return e; }
+
+// range of level l this rank computes
+inline void own_range(const Hierarchy& H, int l, i64& i0, i64& i1) {
+    const Level& L = H.lv[(size_t)l];
+    if (H.comm == nullptr || l >= H.lrep) { i0 = 0; i1 = L.n; }
+    else { i0 = L.parts.lo[H.rank]; i1 = L.parts.lo[H.rank + 1]; }
+}
+// Refreshes the ghost entries of a level-l vector (elements of `esize` bytes) from the two neighbouring ranks:
+// rank r receives [ref_lo[r], lo[r]) from r-1 and [lo[r+1], ref_hi[r]) from r+1, and sends what they reference.
+int exchange_ghosts(const Hierarchy& H, int l, void* vec, size_t esize) {
+    if (H.comm == nullptr || l >= H.lrep) return SSRS_OK;
+    const Level& L = H.lv[(size_t)l];
+    const int r = H.rank, R = H.nparts;
+    const i64 lo = L.parts.lo[r], hi = L.parts.lo[r + 1];
+    i64 su_off = 0, su_n = 0, ru_off = 0, ru_n = 0, sd_off = 0, sd_n = 0, rd_off = 0, rd_n = 0;
+    if (r > 0) {
+        ru_off = L.ref_lo[r]; ru_n = lo - L.ref_lo[r];                  // my upper ghost zone
+        su_off = lo; su_n = L.ref_hi[r - 1] - lo;                       // what rank r-1 references beyond its range
+    }
+    if (r + 1 < R) {
+        rd_off = hi; rd_n = L.ref_hi[r] - hi;
+        sd_off = L.ref_lo[r + 1]; sd_n = hi - L.ref_lo[r + 1];
+    }
+    const i64 e = (i64)esize;
+    if (H.comm->exchange(H.comm->ctx, vec, su_off * e, su_n * e, ru_off * e, ru_n * e, sd_off * e, sd_n * e, rd_off * e, rd_n * e, (void*)H.st) != 0) {
+        set_error("ssrs_potential_solve: halo exchange failed on level %d", l);
+        return SSRS_ERR_CUDA;
+    }
+    return SSRS_OK;
+}
 
 // CSR (float64, diagonal stored) -> sliced ELL (float32)
 int build_ell(Level& L, Pool& pool, stream_t st) {
@@ -596,15 +665,36 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
         excess[i] = (real)(d + off);
         dinv[i] = (real)(1.0 / d);
     }));
+    // row-sharded solve: the index range each part's rows reference (its own range plus the ghost zones)
+    const Parts P = L.parts;
+    for (int q = 0; q < P.n; ++q) { L.ref_lo[q] = P.lo[q]; L.ref_hi[q] = P.lo[q + 1]; }
+    if (P.n > 1) {
+        Pool tmp(st);
+        i64* ref = tmp.get<i64>(2 * P.n);
+        if (!ref) { set_error("ssrs_potential_solve: out of device memory in build_ell"); return SSRS_ERR_CUDA; }
+        i64 init[2 * SSRS_MAX_RANKS];
+        for (int q = 0; q < P.n; ++q) { init[q] = L.ref_lo[q]; init[P.n + q] = L.ref_hi[q]; }
+        AMG_TRY(copy_h2d(ref, init, sizeof(i64) * 2 * (size_t)P.n, st));
+        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+            i64 lo = i, hi = i;
+            for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) { const i64 j = g.col[k]; lo = j < lo ? j : lo; hi = j > hi ? j : hi; }
+            const int q = parts_owner(P, i);
+            if (lo < P.lo[q]) atomic_min_i64(ref + q, lo);
+            if (hi >= P.lo[q + 1]) atomic_max_i64(ref + P.n + q, hi + 1);
+        }));
+        AMG_TRY(copy_d2h(init, ref, sizeof(i64) * 2 * (size_t)P.n, st));
+        AMG_TRY(sync(st));
+        for (int q = 0; q < P.n; ++q) { L.ref_lo[q] = init[q]; L.ref_hi[q] = init[P.n + q]; }
+    }
     return SSRS_OK;
 }
 
 int coarse_solve(Hierarchy& H, Level& C, stream_t st) {
     if (H.coarse_sweeps > 0) {
         const Ell e = ell_of(C);
-        AMG_TRY(ell_first32(e, C.b32, C.x32, H.omega, st));
+        AMG_TRY(ell_first32(e, 0, C.n, C.b32, C.x32, H.omega, st));
         for (int s = 1; s < H.coarse_sweeps; ++s) {
-            AMG_TRY(ell_jacobi32(e, C.b32, C.x32, C.t32, H.omega, st));
+            AMG_TRY(ell_jacobi32(e, 0, C.n, C.b32, C.x32, C.t32, H.omega, st));
             real* sw = C.x32; C.x32 = C.t32; C.t32 = sw;
         }
         return SSRS_OK;
@@ -617,44 +707,97 @@ int coarse_solve(Hierarchy& H, Level& C, stream_t st) {
     });
 }
 
-// out = M^-1 rhs: one V(nu, nu) cycle from a zero guess; rhs must be zero at Dirichlet nodes
+#define AMG_RC(expr) do { const int rc_ = (expr); if (rc_) return rc_; } while (0)
+
+// out = M^-1 rhs: one V(nu, nu) cycle from a zero guess; rhs must be zero at Dirichlet nodes.  In the row-sharded
+// solve rhs/out are valid on the owned rows (rhs ghost rows are refreshed here; out's are not), levels below
+// H.lrep are distributed and every operator application is preceded by a ghost exchange of its input vector.
 int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
     const int nl = (int)H.lv.size(), nu = H.nu;
     const Fine32 F = H.f32;
     const real om = H.omega;
+    const int cols = F.cols;
+    i64 f0, f1;
+    own_range(H, 0, f0, f1);
+    const int r0 = (int)(f0 / cols), r1 = (int)(f1 / cols);
+    AMG_RC(exchange_ghosts(H, 0, (void*)rhs, sizeof(double)));
     if (nl == 1) {          // no coarse level: plain Jacobi sweeps
-        AMG_TRY(fine_first32(F, rhs, H.xf, om, st));
-        for (int s = 1; s < 2 * nu - 1; ++s) { AMG_TRY(fine_jacobi32(F, rhs, H.xf, H.tf, om, st)); real* sw = H.xf; H.xf = H.tf; H.tf = sw; }
-        return fine_jacobi32(F, rhs, H.xf, out, om, st);
-    }
-    if (nu == 1) { AMG_TRY(fine_first_residual32(F, rhs, H.xf, H.resf, om, st)); }
-    else {
-        AMG_TRY(fine_first32(F, rhs, H.xf, om, st));
-        for (int s = 1; s < nu; ++s) { AMG_TRY(fine_jacobi32(F, rhs, H.xf, H.tf, om, st)); real* sw = H.xf; H.xf = H.tf; H.tf = sw; }
-        AMG_TRY(fine_residual32(F, rhs, H.xf, H.resf, st));
-    }
-    AMG_TRY(restrict32(H.lv[0], H.resf, H.lv[1].b32, st));
-    for (int l = 1; l < nl - 1; ++l) {
-        Level& L = H.lv[l];
-        const Ell e = ell_of(L);
-        if (nu == 1) { AMG_TRY(ell_first_residual32(e, L.b32, L.x32, L.r32, om, st)); }
-        else {
-            AMG_TRY(ell_first32(e, L.b32, L.x32, om, st));
-            for (int s = 1; s < nu; ++s) { AMG_TRY(ell_jacobi32(e, L.b32, L.x32, L.t32, om, st)); real* sw = L.x32; L.x32 = L.t32; L.t32 = sw; }
-            AMG_TRY(ell_residual32(e, L.b32, L.x32, L.r32, st));
+        AMG_TRY(fine_first32(F, r0, r1, rhs, H.xf, om, st));
+        for (int s = 1; s < 2 * nu - 1; ++s) {
+            AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
+            AMG_TRY(fine_jacobi32(F, r0, r1, rhs, H.xf, H.tf, om, st));
+            real* sw = H.xf; H.xf = H.tf; H.tf = sw;
         }
-        AMG_TRY(restrict32(L, L.r32, H.lv[l + 1].b32, st));
+        AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
+        return fine_jacobi32(F, r0, r1, rhs, H.xf, out, om, st);
     }
-    { int rc = coarse_solve(H, H.lv[nl - 1], st); if (rc) return rc; }
-    for (int l = nl - 2; l >= 1; --l) {
-        Level& L = H.lv[l];
+    if (nu == 1) { AMG_TRY(fine_first_residual32(F, r0, r1, rhs, H.xf, H.resf, om, st)); }
+    else {
+        AMG_TRY(fine_first32(F, r0, r1, rhs, H.xf, om, st));
+        for (int s = 1; s < nu; ++s) {
+            AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
+            AMG_TRY(fine_jacobi32(F, r0, r1, rhs, H.xf, H.tf, om, st));
+            real* sw = H.xf; H.xf = H.tf; H.tf = sw;
+        }
+        AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
+        AMG_TRY(fine_residual32(F, r0, r1, rhs, H.xf, H.resf, st));
+    }
+    // restriction to level l+1 covers the aggregates this rank owns there (all of their members are local);
+    // entering the redundantly computed levels the pieces are gathered on every rank
+    auto restrict_to = [&](int l, const real* res) -> int {
+        Level& C = H.lv[(size_t)l + 1];
+        i64 c0 = 0, c1 = C.n;
+        const bool gather = H.comm != nullptr && l < H.lrep && l + 1 >= H.lrep;
+        if (H.comm != nullptr && l < H.lrep) { c0 = C.parts.lo[H.rank]; c1 = C.parts.lo[H.rank + 1]; }
+        AMG_TRY(restrict32(H.lv[(size_t)l], c0, c1, res, C.b32, st));
+        if (gather) {
+            i64 offs[SSRS_MAX_RANKS + 1];
+            for (int q = 0; q <= H.nparts; ++q) offs[q] = C.parts.lo[q] * (i64)sizeof(real);
+            if (H.comm->allgather(H.comm->ctx, C.b32, offs, (void*)st) != 0) { set_error("ssrs_potential_solve: all-gather failed on level %d", l + 1); return SSRS_ERR_CUDA; }
+        }
+        return SSRS_OK;
+    };
+    AMG_RC(restrict_to(0, H.resf));
+    for (int l = 1; l < nl - 1; ++l) {
+        Level& L = H.lv[(size_t)l];
         const Ell e = ell_of(L);
-        AMG_TRY(prolong_add32(L, L.n, L.x32, H.lv[l + 1].x32, H.overcorrect, st));
-        for (int s = 0; s < nu; ++s) { AMG_TRY(ell_jacobi32(e, L.b32, L.x32, L.t32, om, st)); real* sw = L.x32; L.x32 = L.t32; L.t32 = sw; }
+        i64 i0, i1;
+        own_range(H, l, i0, i1);
+        AMG_RC(exchange_ghosts(H, l, L.b32, sizeof(real)));
+        if (nu == 1) { AMG_TRY(ell_first_residual32(e, i0, i1, L.b32, L.x32, L.r32, om, st)); }
+        else {
+            AMG_TRY(ell_first32(e, i0, i1, L.b32, L.x32, om, st));
+            for (int s = 1; s < nu; ++s) {
+                AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
+                AMG_TRY(ell_jacobi32(e, i0, i1, L.b32, L.x32, L.t32, om, st));
+                real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
+            }
+            AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
+            AMG_TRY(ell_residual32(e, i0, i1, L.b32, L.x32, L.r32, st));
+        }
+        AMG_RC(restrict_to(l, L.r32));
     }
-    AMG_TRY(prolong_add32(H.lv[0], H.fine.size(), H.xf, H.lv[1].x32, H.overcorrect, st));
-    for (int s = 0; s < nu - 1; ++s) { AMG_TRY(fine_jacobi32(F, rhs, H.xf, H.tf, om, st)); real* sw = H.xf; H.xf = H.tf; H.tf = sw; }
-    return fine_jacobi32(F, rhs, H.xf, out, om, st);
+    AMG_RC(coarse_solve(H, H.lv[(size_t)nl - 1], st));
+    for (int l = nl - 2; l >= 1; --l) {
+        Level& L = H.lv[(size_t)l];
+        const Ell e = ell_of(L);
+        i64 i0, i1;
+        own_range(H, l, i0, i1);
+        AMG_TRY(prolong_add32(L, i0, i1, L.x32, H.lv[(size_t)l + 1].x32, H.overcorrect, st));
+        for (int s = 0; s < nu; ++s) {
+            AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
+            AMG_TRY(ell_jacobi32(e, i0, i1, L.b32, L.x32, L.t32, om, st));
+            real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
+        }
+    }
+    AMG_TRY(prolong_add32(H.lv[0], f0, f1, H.xf, H.lv[1].x32, H.overcorrect, st));
+    for (int s = 0; s < nu - 1; ++s) {
+        AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
+        AMG_TRY(fine_jacobi32(F, r0, r1, rhs, H.xf, H.tf, om, st));
+        real* sw = H.xf; H.xf = H.tf; H.tf = sw;
+    }
+    AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
+    return fine_jacobi32(F, r0, r1, rhs, H.xf, out, om, st);
 }
 
 int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
@@ -690,9 +833,9 @@ int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
 }
 
 // out = b - A x at free nodes (b = 0 there: the Dirichlet values live in x), 0 at Dirichlet nodes; *nrm2 = |out|^2
-int fine_residual(const FineGraph fg, const FineWeights W, const double* x, double* out, double* nrm2, stream_t st) {
+int fine_residual(const FineGraph fg, const FineWeights W, int r0, int r1, const double* x, double* out, double* nrm2, stream_t st) {
     double dummy;
-    AMG_TRY(preduce2d_sum2(fg.rows, fg.cols, st, nrm2, &dummy, [=] SSRS_HD(int r, int c, double& u0, double& u1) {
+    AMG_TRY(preduce2d_sum2_rows(r0, r1, fg.cols, st, nrm2, &dummy, [=] SSRS_HD(int r, int c, double& u0, double& u1) {
         const i64 i = (i64)r * fg.cols + c;
         const double v = fg.excluded(i) ? 0.0 : -fine_apply64(fg, W, r, c, x);
         out[i] = v;
@@ -701,9 +844,9 @@ int fine_residual(const FineGraph fg, const FineWeights W, const double* x, doub
     return SSRS_OK;
 }
 // out = A in for a correction vector `in` (zero at Dirichlet nodes); *d0 = <w0, out>, *d1 = <out, out>
-int fine_apply_dots(const FineGraph fg, const FineWeights W, const double* in, double* out, const double* w0,
+int fine_apply_dots(const FineGraph fg, const FineWeights W, int r0, int r1, const double* in, double* out, const double* w0,
                     double* d0, double* d1, stream_t st) {
-    AMG_TRY(preduce2d_sum2(fg.rows, fg.cols, st, d0, d1, [=] SSRS_HD(int r, int c, double& u0, double& u1) {
+    AMG_TRY(preduce2d_sum2_rows(r0, r1, fg.cols, st, d0, d1, [=] SSRS_HD(int r, int c, double& u0, double& u1) {
         const i64 i = (i64)r * fg.cols + c;
         const double v = fg.excluded(i) ? 0.0 : fine_apply64(fg, W, r, c, in);
         out[i] = v;
@@ -724,19 +867,30 @@ using namespace ssrs::amg;
 
 #ifdef SSRS_HOST_EMU
 #define SOLVE_NAME ssrs_emu_potential_solve
+#define SOLVE_SHARDED_NAME ssrs_emu_potential_solve_sharded
 extern "C" __attribute__((visibility("default"))) const char* ssrs_emu_last_error(void) { return ssrs::g_emu_err; }
 #else
 #define SOLVE_NAME ssrs_potential_solve
+#define SOLVE_SHARDED_NAME ssrs_potential_solve_sharded
 #endif
 
 namespace ssrs { namespace amg {
 int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, const double* bvalues_host,
-               int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats, void* stream) {
+               int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats, const ssrs_comm* comm,
+               void* stream) {
+    if (comm != nullptr && comm->size <= 1) comm = nullptr;
+    if (comm != nullptr) {
+        if (comm->size > SSRS_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->size || !comm->exchange || !comm->allreduce_sum || !comm->allgather) {
+            set_error("ssrs_potential_solve_sharded: bad communicator (size %d, rank %d)", comm->size, comm->rank);
+            return SSRS_ERR_INVALID;
+        }
+        if (rows < 4 * comm->size) { set_error("ssrs_potential_solve_sharded: %d rows cannot be split over %d ranks", rows, comm->size); return SSRS_ERR_INVALID; }
+    }
     if (K == nullptr || phi == nullptr) { set_error("ssrs_potential_solve: NULL raster"); return SSRS_ERR_INVALID; }
     if (rows < 3 || cols < 3) { set_error("ssrs_potential_solve: grid %dx%d too small", rows, cols); return SSRS_ERR_INVALID; }
     if ((int64_t)rows * cols > 2000000000LL) { set_error("ssrs_potential_solve: more than 2e9 cells"); return SSRS_ERR_UNSUPPORTED; }
     if (n_bnodes <= 0 || bnodes_host == nullptr || bvalues_host == nullptr) { set_error("ssrs_potential_solve: no Dirichlet nodes"); return SSRS_ERR_INVALID; }
-    if (!(rtol > 0.0)) rtol = 1e-9;
+    if (!(rtol > 0.0)) rtol = 0.0;          // default: iterate to the attainable accuracy (see below)
     if (max_iter <= 0) max_iter = 300;
     stream_t st = (stream_t)stream;
     const i64 n = (i64)rows * cols;
@@ -794,6 +948,21 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         if (rr > 0 && rr < rows - 1 && cc > 0 && cc < cols - 1) { interior = 1; break; }
     }
     H.fine.kd = kd; H.fine.rows = rows; H.fine.cols = cols; H.fine.interior_dirichlet = interior;
+    H.comm = comm; H.st = st;
+    H.lv.emplace_back();
+    H.lv[0].n = n;
+    if (comm != nullptr) {          // contiguous row slabs; the fine level's ghost zone is one row on each side
+        H.rank = comm->rank; H.nparts = comm->size;
+        Parts P;
+        P.n = comm->size;
+        for (int q = 0; q <= P.n; ++q) P.lo[q] = (i64)((int64_t)rows * q / P.n) * cols;
+        H.fine.parts = P;
+        H.lv[0].parts = P;
+        for (int q = 0; q < P.n; ++q) {
+            H.lv[0].ref_lo[q] = q > 0 ? P.lo[q] - cols : 0;
+            H.lv[0].ref_hi[q] = q + 1 < P.n ? P.lo[q + 1] + cols : n;
+        }
+    }
     {
         float* wf; real* dinv; double* wd;
         AMG_ALLOC(wf, float, 4 * n);
@@ -836,13 +1005,12 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     // ---- setup: hierarchy ----
     const double theta = 0.5;
     const i64 coarse_target = 400, dense_cap = 2048;
-    H.lv.emplace_back();
-    H.lv[0].n = n;
     i64 total_nnz = 9 * n, ell_total = 0;
     for (int l = 0; l < 40; ++l) {
         Level& L = H.lv[(size_t)l];
         if (l > 0 && L.n <= coarse_target) break;
-        int rc = (l == 0) ? coarsen(H.fine, L, pool, theta, 8, 3, st) : coarsen(csr_of(L), L, pool, theta, 8, 3, st);
+        Parts next;
+        int rc = (l == 0) ? coarsen(H.fine, L, pool, theta, 8, 3, &next, st) : coarsen(csr_of(L), L, pool, theta, 8, 3, &next, st);
         if (rc) return rc;
         if (L.nc < 1 || (double)L.nc > 0.9 * (double)L.n) {        // stalled: stop here
             pool.release(L.agg); pool.release(L.memptr); pool.release(L.mem);
@@ -853,6 +1021,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         rc = (l == 0) ? galerkin(H.fine, L, C, pool, st) : galerkin(csr_of(L), L, C, pool, st);
         if (rc) return rc;
         total_nnz += C.nnz;
+        C.parts = next;
         rc = build_ell(C, pool, st);
         if (rc) return rc;
         ell_total += C.ell_entries;
@@ -865,18 +1034,54 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             else H.coarse_sweeps = 60;
         }
     }
+    if (comm != nullptr) {
+        // Levels are distributed while they are large and every part's rows reference the adjacent parts only;
+        // from the first level that is not, all ranks compute redundantly.  The coarsest level is always redundant.
+        const i64 rep_rows = getenv("SSRS_X_REPROWS") ? atoll(getenv("SSRS_X_REPROWS")) : 65536;
+        const int nl = (int)H.lv.size();
+        int lrep = nl - 1;
+        for (int l = 1; l < nl; ++l) {
+            const Level& L = H.lv[(size_t)l];
+            bool ok = L.n >= rep_rows;
+            for (int q = 0; q < L.parts.n && ok; ++q) {
+                if (q > 0 && L.ref_lo[q] < L.parts.lo[q - 1]) ok = false;
+                if (q + 1 < L.parts.n && L.ref_hi[q] > L.parts.lo[q + 2]) ok = false;
+            }
+            if (!ok) { lrep = l; break; }
+        }
+        H.lrep = lrep < 1 ? 1 : lrep;
+        if (trace) fprintf(stderr, "ssrs_potential_solve: rank %d of %d, levels %d, redundant from level %d\n", H.rank, H.nparts, nl, H.lrep);
+    }
     const double t_setup = now_ms();
 
     // ---- BiCGStab, right preconditioned ----
+    // Row-sharded: every vector operation covers the owned rows [R0, R1) (cells [I0, I1)); inner products are
+    // summed over the ranks (bit-identical on every rank, so all ranks take the same branches); an operator's
+    // input gets its ghost rows refreshed first.
     const FineGraph fg = H.fine;
+    i64 I0, I1;
+    own_range(H, 0, I0, I1);
+    const int R0 = (int)(I0 / cols), R1 = (int)(I1 / cols);
+    auto allsum = [&](double* a, double* b) -> int {
+        if (comm == nullptr) return 0;
+        double h[2] = {*a, b ? *b : 0.0};
+        if (comm->allreduce_sum(comm->ctx, h, 2, (void*)st) != 0) { set_error("ssrs_potential_solve: all-reduce failed"); return SSRS_ERR_CUDA; }
+        *a = h[0]; if (b) *b = h[1];
+        return 0;
+    };
+    auto true_residual = [&](double* out, double* nrm2) -> int {
+        AMG_RC(exchange_ghosts(H, 0, x, sizeof(double)));
+        AMG_RC(fine_residual(fg, H.fw, R0, R1, x, out, nrm2, st));
+        return allsum(nrm2, nullptr);
+    };
     double r0n2 = 0.0;
-    { int rc = fine_residual(fg, H.fw, x, r, &r0n2, st); if (rc) return rc; }
+    AMG_RC(true_residual(r, &r0n2));
     const double r0 = sqrt(r0n2);
     // Attainable accuracy: the nearest float64-representable potential leaves a residual of about
     // d_i * ulp(phi_i) / 2 per cell (d_i = row diagonal); below that the recurrence residual keeps falling but
     // the true one does not (the estimate is 1.5-4x above the floor measured on 300 k .. 30 M cell grids).  The
     // recurrence residual is iterated to the larger of rtol and floor/8 — it tracks the error for a while after
-    // the true residual has flattened — and the result is accepted when the true residual is within 2x the floor.
+    // the true residual has flattened — and the result is accepted when the true residual is below floor/2.
     double floor2 = 0.0, bmax = 0.0;
     for (int64_t q = 0; q < n_bnodes; ++q) bmax = fabs(bvalues_host[q]) > bmax ? fabs(bvalues_host[q]) : bmax;
     { const real* dinv = H.f32.dinv; const double scale = 0.5 * 2.220446049250313e-16 * bmax;
@@ -885,79 +1090,77 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     if (trace) fprintf(stderr, "ssrs_potential_solve: r0 %.3e attainable relative residual ~ %.3e\n", r0, floor_rel);
     const double floor_frac = getenv("SSRS_X_FLOORFRAC") ? atof(getenv("SSRS_X_FLOORFRAC")) : 0.125;
     const double accept_frac = getenv("SSRS_X_ACCEPT") ? atof(getenv("SSRS_X_ACCEPT")) : 0.5;
-    const int repl_mode = getenv("SSRS_X_REPL") ? atoi(getenv("SSRS_X_REPL")) : 0;
-    const double repl_drop = getenv("SSRS_X_REPLDROP") ? atof(getenv("SSRS_X_REPLDROP")) : 0.1;
-    int replacements = 0;
     const double tol_eff = rtol > floor_frac * floor_rel ? rtol : floor_frac * floor_rel;
     int iters = 0, restarts = 0, converged = (r0 == 0.0);
     double best_true = 1.0;
     double rel = (r0 == 0.0) ? 0.0 : 1.0;
+    const size_t own_bytes = sizeof(double) * (size_t)(I1 - I0);
     while (!converged && iters < max_iter && restarts <= 6) {
-        AMG_TRY(copy_d2d(rh, r, sizeof(double) * (size_t)n, st));
-        AMG_TRY(dev_zero(p, sizeof(double) * (size_t)n, st));
-        AMG_TRY(dev_zero(v, sizeof(double) * (size_t)n, st));
-        double rho = 1.0, alpha = 1.0, om = 1.0, rho_new = 0.0, peak = rel;
+        AMG_TRY(copy_d2d(rh + I0, r + I0, own_bytes, st));
+        AMG_TRY(dev_zero(p + I0, own_bytes, st));
+        AMG_TRY(dev_zero(v + I0, own_bytes, st));
+        double rho = 1.0, alpha = 1.0, om = 1.0, rho_new = 0.0;
         bool breakdown = false;
-        { const double *a_ = rh, *b_ = r; AMG_TRY(preduce_sum(n, st, &rho_new, [=] SSRS_HD(i64 i) { return a_[i] * b_[i]; })); }
+        { const double *a_ = rh, *b_ = r; AMG_TRY(preduce_sum_range(I0, I1, st, &rho_new, [=] SSRS_HD(i64 i) { return a_[i] * b_[i]; })); }
+        AMG_RC(allsum(&rho_new, nullptr));
         while (iters < max_iter) {
             if (rho_new == 0.0 || !(fabs(rho_new) < 1e300)) { breakdown = true; break; }
             const double beta = (rho_new / rho) * (alpha / om);
             rho = rho_new;
             { double *pp = p; const double *rr = r, *vv = v; const double om_ = om;
-              AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) { pp[i] = rr[i] + beta * (pp[i] - om_ * vv[i]); })); }
-            { int rc = vcycle(H, p, y, st); if (rc) return rc; }
+              AMG_TRY(pfor_range(I0, I1, st, [=] SSRS_HD(i64 i) { pp[i] = rr[i] + beta * (pp[i] - om_ * vv[i]); })); }
+            AMG_RC(vcycle(H, p, y, st));
             double rhv = 0.0, vv2 = 0.0;
-            { int rc = fine_apply_dots(fg, H.fw, y, v, rh, &rhv, &vv2, st); if (rc) return rc; }
+            AMG_RC(exchange_ghosts(H, 0, y, sizeof(double)));
+            AMG_RC(fine_apply_dots(fg, H.fw, R0, R1, y, v, rh, &rhv, &vv2, st));
+            AMG_RC(allsum(&rhv, nullptr));
             if (rhv == 0.0) { breakdown = true; break; }
             alpha = rho / rhv;
             { double* ss = s; const double *rr = r, *vv = v; const double al = alpha;
-              AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) { ss[i] = rr[i] - al * vv[i]; })); }
-            { int rc = vcycle(H, s, z, st); if (rc) return rc; }
+              AMG_TRY(pfor_range(I0, I1, st, [=] SSRS_HD(i64 i) { ss[i] = rr[i] - al * vv[i]; })); }
+            AMG_RC(vcycle(H, s, z, st));
             double ts = 0.0, tt = 0.0;
-            { int rc = fine_apply_dots(fg, H.fw, z, t, s, &ts, &tt, st); if (rc) return rc; }
+            AMG_RC(exchange_ghosts(H, 0, z, sizeof(double)));
+            AMG_RC(fine_apply_dots(fg, H.fw, R0, R1, z, t, s, &ts, &tt, st));
+            AMG_RC(allsum(&ts, &tt));
             om = (tt > 0.0) ? ts / tt : 0.0;
             double rn2 = 0.0;
             { double *xx = x, *rr = r; const double *yy = y, *zz = z, *ss = s, *tv = t, *rh_ = rh; const double al = alpha, om_ = om;
-              AMG_TRY(preduce_sum2(n, st, &rn2, &rho_new, [=] SSRS_HD(i64 i, double& u0, double& u1) {
+              AMG_TRY(preduce_sum2_range(I0, I1, st, &rn2, &rho_new, [=] SSRS_HD(i64 i, double& u0, double& u1) {
                   xx[i] += al * yy[i] + om_ * zz[i];
                   const double rv = ss[i] - om_ * tv[i];
                   rr[i] = rv;
                   u0 = rv * rv; u1 = rh_[i] * rv;
               })); }
+            AMG_RC(allsum(&rn2, &rho_new));
             ++iters;
             rel = sqrt(rn2) / r0;
             if (trace) {
                 double tr2 = 0.0;
-                { int rc = fine_residual(fg, H.fw, x, t, &tr2, st); if (rc) return rc; }
+                AMG_RC(true_residual(t, &tr2));
                 fprintf(stderr, "ssrs_potential_solve: iter %d rel %.3e true %.3e alpha %.3e omega %.3e\n", iters, rel, sqrt(tr2) / r0, alpha, om);
             }
             if (!(rel == rel)) { breakdown = true; break; }
             if (rel <= tol_eff || om == 0.0) break;
-            if (rel > peak) peak = rel;
-            if (repl_mode == 1 && rel < repl_drop * peak && rel > 4.0 * tol_eff) {
-                // residual replacement: the recurrence residual has come down from a peak; peaks are where the
-                // gap to the true residual opens (rounding scales with the largest intermediate vectors)
-                double tr2 = 0.0;
-                { int rc = fine_residual(fg, H.fw, x, r, &tr2, st); if (rc) return rc; }
-                { const double *a_ = rh, *b_ = r; AMG_TRY(preduce_sum(n, st, &rho_new, [=] SSRS_HD(i64 i) { return a_[i] * b_[i]; })); }
-                peak = sqrt(tr2) / r0;
-                ++replacements;
-                if (trace) fprintf(stderr, "ssrs_potential_solve:   residual replaced, true %.3e\n", peak);
-            }
         }
         // true residual: accept, or restart from the current iterate
         double tn2 = 0.0;
-        { int rc = fine_residual(fg, H.fw, x, r, &tn2, st); if (rc) return rc; }
+        AMG_RC(true_residual(r, &tn2));
         rel = sqrt(tn2) / r0;
         if (trace) fprintf(stderr, "ssrs_potential_solve: true residual %.3e after %d iterations\n", rel, iters);
         if (!(rel == rel)) { set_error("ssrs_potential_solve: NaN residual (NaN in the conductivity raster?)"); return SSRS_ERR_NOT_CONVERGED; }
-        if (rel <= 4.0 * rtol) converged = 1;
-        else if (rel <= accept_frac * floor_rel) converged = 2;                                   // float64 attainable accuracy reached
-        else if (!breakdown && rel > 0.5 * best_true && rel <= 1e-6) converged = 2;   // float64 attainable accuracy reached
+        if (rtol > 0.0 && rel <= 4.0 * rtol) converged = 1;
+        else if (rel <= accept_frac * floor_rel) converged = 2;                       // float64 attainable accuracy reached
+        else if (!breakdown && rel > 0.5 * best_true && rel <= 1e-6) converged = 2;   // stagnated there
         else ++restarts;
         if (rel < best_true) best_true = rel;
     }
-    { const double* xx = x; AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) { phi[i] = (float)xx[i]; })); }     // movmodel.py:128
+    { const double* xx = x; AMG_TRY(pfor_range(I0, I1, st, [=] SSRS_HD(i64 i) { phi[i] = (float)xx[i]; })); }     // movmodel.py:128
+    if (comm != nullptr) {          // every rank returns the full raster (the stepping stage replicates the fields)
+        i64 offs[SSRS_MAX_RANKS + 1];
+        for (int q = 0; q <= H.nparts; ++q) offs[q] = H.lv[0].parts.lo[q] * (i64)sizeof(float);
+        if (comm->allgather(comm->ctx, phi, offs, (void*)st) != 0) { set_error("ssrs_potential_solve: all-gather of the potential failed"); return SSRS_ERR_CUDA; }
+    }
     AMG_TRY(sync(st));
     const double t_end = now_ms();
     if (stats) {
@@ -980,5 +1183,11 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
 extern "C" __attribute__((visibility("default")))
 int SOLVE_NAME(const float* K, int rows, int cols, const int64_t* bnodes_host, const double* bvalues_host,
                int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats, void* stream) {
-    return ssrs::amg::solve_impl(K, rows, cols, bnodes_host, bvalues_host, n_bnodes, rtol, max_iter, phi, stats, stream);
+    return ssrs::amg::solve_impl(K, rows, cols, bnodes_host, bvalues_host, n_bnodes, rtol, max_iter, phi, stats, nullptr, stream);
+}
+extern "C" __attribute__((visibility("default")))
+int SOLVE_SHARDED_NAME(const float* K, int rows, int cols, const int64_t* bnodes_host, const double* bvalues_host,
+                       int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats,
+                       const ssrs_comm* comm, void* stream) {
+    return ssrs::amg::solve_impl(K, rows, cols, bnodes_host, bvalues_host, n_bnodes, rtol, max_iter, phi, stats, comm, stream);
 }

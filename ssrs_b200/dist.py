@@ -4,6 +4,10 @@ The path shards naturally: tracks are block-partitioned by glob
 and the only exchange is one sum all-reduce of the presence raster per (case, realisation).  Because the RNG
 is keyed by (seed, global track id, step) and counts are integers, results are bit-identical for any number
 of ranks.  Everything degrades to a no-op in a single process.
+
+The row-sharded potential solve (BASELINE config 5) and `ssrs_presence_allreduce` use the library's own NCCL
+communicator (`native_comm()`, `ssrs_comm` in include/ssrs_b200.h); torch.distributed only carries the 128-byte
+NCCL id from rank 0 to the others.
 """
 from __future__ import annotations
 
@@ -52,3 +56,53 @@ def gather_tracks(tracks):
     parts = [None] * d.get_world_size()
     d.all_gather_object(parts, tracks)
     return [t for p in parts for t in p]
+
+
+_native_comm = None
+
+
+def native_comm():
+    """The library's NCCL communicator (`ssrs_comm*` as a ctypes void pointer) spanning the torch.distributed
+    world, created once per process; None in a single process.  Collective: every rank must call it."""
+    global _native_comm
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return None
+    if _native_comm is None:
+        import ctypes as C
+
+        from . import _native as N
+        torch = N.require_cuda()
+        lib = N.load()
+        buf = (C.c_uint8 * 128)()
+        if d.get_rank() == 0:
+            N.check(lib.ssrs_nccl_unique_id(buf), "ssrs_nccl_unique_id")
+        box = [bytes(buf)]
+        d.broadcast_object_list(box, src=0)
+        C.memmove(buf, box[0], 128)
+        torch.cuda.synchronize()
+        out = C.c_void_p()
+        N.check(lib.ssrs_comm_create_nccl(buf, d.get_rank(), d.get_world_size(), C.byref(out)), "ssrs_comm_create_nccl")
+        _native_comm = out
+    return _native_comm
+
+
+def destroy_native_comm() -> None:
+    global _native_comm
+    if _native_comm is not None:
+        from . import _native as N
+        N.load().ssrs_comm_destroy(_native_comm)
+        _native_comm = None
+
+
+def presence_allreduce(presence):
+    """In-place sum of a CUDA int32/uint32 presence raster over all ranks through `ssrs_presence_allreduce`."""
+    comm = native_comm()
+    if comm is None:
+        return presence
+    from . import _native as N
+    if not presence.is_cuda or presence.element_size() != 4 or not presence.is_contiguous():
+        raise ValueError("presence must be a contiguous CUDA raster of 32-bit counts")
+    N.check(N.load().ssrs_presence_allreduce(N.ptr(presence), presence.numel(), comm, N.current_stream()),
+            "ssrs_presence_allreduce")
+    return presence

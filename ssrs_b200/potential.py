@@ -27,7 +27,7 @@ class SolveStats(C.Structure):
                 "workspace_bytes": int(self.workspace_bytes)}
 
 
-def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict):
+def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict, comm=None):
     torch = N.require_cuda()
     lib = N.load()
     rows, cols = K_dev.shape
@@ -37,9 +37,14 @@ def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict):
         raise ValueError("bnodes and benergy must be 1-D arrays of equal length")
     phi = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
     st = SolveStats()
-    rc = lib.ssrs_potential_solve(N.ptr(K_dev), rows, cols, bn.ctypes.data_as(C.POINTER(C.c_int64)),
-                                  bv.ctypes.data_as(C.POINTER(C.c_double)), bn.size, float(rtol), int(max_iter),
-                                  N.ptr(phi), C.byref(st), N.current_stream())
+    if comm is None:
+        rc = lib.ssrs_potential_solve(N.ptr(K_dev), rows, cols, bn.ctypes.data_as(C.POINTER(C.c_int64)),
+                                      bv.ctypes.data_as(C.POINTER(C.c_double)), bn.size, float(rtol), int(max_iter),
+                                      N.ptr(phi), C.byref(st), N.current_stream())
+    else:
+        rc = lib.ssrs_potential_solve_sharded(N.ptr(K_dev), rows, cols, bn.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              bv.ctypes.data_as(C.POINTER(C.c_double)), bn.size, float(rtol),
+                                              int(max_iter), N.ptr(phi), C.byref(st), comm, N.current_stream())
     stats = st.as_dict()
     if rc == -4 and not strict:                       # SSRS_ERR_NOT_CONVERGED: potential was still written
         print(f"ssrs_b200: potential solve stopped at relative residual {stats['rel_residual']:.2e}")
@@ -48,9 +53,13 @@ def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict):
     return phi, stats
 
 
-def solve_potential_device(conductivity, move_dirn: float, rtol: float = 0.0, max_iter: int = 0, strict: bool = True):
+def solve_potential_device(conductivity, move_dirn: float, rtol: float = 0.0, max_iter: int = 0, strict: bool = True,
+                           sharded: bool = False):
     """K: CUDA float32 tensor [rows, cols] (or array-like) -> (phi CUDA float32 tensor, stats dict).
-    Dirichlet sets come from `MovModel(move_dirn, shape).get_boundary_nodes()`."""
+    Dirichlet sets come from `MovModel(move_dirn, shape).get_boundary_nodes()`.
+    sharded=True (collective over the torch.distributed world; every rank passes the same K): the solve phase is
+    row-sharded over the ranks with NCCL halo exchanges (`ssrs_potential_solve_sharded`); every rank gets the
+    full potential."""
     torch = N.require_cuda()
     from .movmodel import MovModel
     if isinstance(conductivity, torch.Tensor):
@@ -60,7 +69,11 @@ def solve_potential_device(conductivity, move_dirn: float, rtol: float = 0.0, ma
     if K.dim() != 2:
         raise ValueError("conductivity must be a 2-D raster")
     bn, bv = MovModel(move_dirn, tuple(K.shape)).get_boundary_nodes()
-    return _solve(K, bn, bv, rtol, max_iter, strict)
+    comm = None
+    if sharded:
+        from . import dist as D
+        comm = D.native_comm()
+    return _solve(K, bn, bv, rtol, max_iter, strict, comm)
 
 
 def solve_potential_nodes(conductivity, bnodes, benergy, rtol: float = 0.0, max_iter: int = 0, return_stats: bool = False):

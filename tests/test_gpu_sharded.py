@@ -1,0 +1,28 @@
+"""Row-sharded potential solve + presence all-reduce over the library's NCCL communicator on 2 GPUs
+(skipped on a single-GPU box; CPU coverage of the same solver code: tests/test_solver_sharded_cpu.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_sharded_solve_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29500 + os.getpid() % 400
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "sharded_solve_run.py"), "1500", "1800", "30", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["sharded"]["converged"] in (1, 2)
+    assert out["max_abs_diff_vs_single"] <= 2 * float(np.spacing(np.float32(1000.0)))     # float32-rounding level
+    assert out["identical_on_all_ranks"] and out["presence_allreduce_ok"]
