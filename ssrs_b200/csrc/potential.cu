@@ -951,10 +951,11 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     H.comm = comm; H.st = st;
     H.lv.emplace_back();
     H.lv[0].n = n;
-    if (comm != nullptr) {          // contiguous row slabs; the fine level's ghost zone is one row on each side
-        H.rank = comm->rank; H.nparts = comm->size;
+    const int fake_parts = (comm == nullptr && getenv("SSRS_X_FAKEPARTS")) ? atoi(getenv("SSRS_X_FAKEPARTS")) : 0;   // experiment: slab-constrained coarsening on one rank
+    if (comm != nullptr || fake_parts > 1) {          // contiguous row slabs; the fine level's ghost zone is one row on each side
+        if (comm != nullptr) { H.rank = comm->rank; H.nparts = comm->size; }
         Parts P;
-        P.n = comm->size;
+        P.n = comm != nullptr ? comm->size : fake_parts;
         for (int q = 0; q <= P.n; ++q) P.lo[q] = (i64)((int64_t)rows * q / P.n) * cols;
         H.fine.parts = P;
         H.lv[0].parts = P;
@@ -1006,11 +1007,27 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     const double theta = 0.5;
     const i64 coarse_target = 400, dense_cap = 2048;
     i64 total_nnz = 9 * n, ell_total = 0;
+    // Row-sharded solve: a level stays distributed while it is large and every part's rows reference the
+    // adjacent parts only; its aggregates must then not straddle a slab boundary.  From the first level that is
+    // not (H.lrep) all ranks compute redundantly and coarsening is unconstrained again — constraining every
+    // level leaves a seam that the coarse levels never close and costs ~40 % more iterations.
+    const i64 rep_rows = getenv("SSRS_X_REPROWS") ? atoll(getenv("SSRS_X_REPROWS")) : 65536;
+    bool distributed = H.lv[0].parts.n > 1;
     for (int l = 0; l < 40; ++l) {
         Level& L = H.lv[(size_t)l];
         if (l > 0 && L.n <= coarse_target) break;
+        if (distributed && l > 0) {
+            bool ok = L.n >= rep_rows;
+            for (int q = 0; q < L.parts.n && ok; ++q) {
+                if (q > 0 && L.ref_lo[q] < L.parts.lo[q - 1]) ok = false;
+                if (q + 1 < L.parts.n && L.ref_hi[q] > L.parts.lo[q + 2]) ok = false;
+            }
+            if (!ok) { distributed = false; H.lrep = l; }
+        }
         Parts next;
-        int rc = (l == 0) ? coarsen(H.fine, L, pool, theta, 8, 3, &next, st) : coarsen(csr_of(L), L, pool, theta, 8, 3, &next, st);
+        int rc;
+        if (l == 0) { FineGraph g = H.fine; if (!distributed) g.parts = Parts(); rc = coarsen(g, L, pool, theta, 8, 3, &next, st); }
+        else { CsrGraph g = csr_of(L); if (!distributed) g.parts = Parts(); rc = coarsen(g, L, pool, theta, 8, 3, &next, st); }
         if (rc) return rc;
         if (L.nc < 1 || (double)L.nc > 0.9 * (double)L.n) {        // stalled: stop here
             pool.release(L.agg); pool.release(L.memptr); pool.release(L.mem);
@@ -1034,23 +1051,11 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             else H.coarse_sweeps = 60;
         }
     }
-    if (comm != nullptr) {
-        // Levels are distributed while they are large and every part's rows reference the adjacent parts only;
-        // from the first level that is not, all ranks compute redundantly.  The coarsest level is always redundant.
-        const i64 rep_rows = getenv("SSRS_X_REPROWS") ? atoll(getenv("SSRS_X_REPROWS")) : 65536;
+    if (H.lv[0].parts.n > 1) {
         const int nl = (int)H.lv.size();
-        int lrep = nl - 1;
-        for (int l = 1; l < nl; ++l) {
-            const Level& L = H.lv[(size_t)l];
-            bool ok = L.n >= rep_rows;
-            for (int q = 0; q < L.parts.n && ok; ++q) {
-                if (q > 0 && L.ref_lo[q] < L.parts.lo[q - 1]) ok = false;
-                if (q + 1 < L.parts.n && L.ref_hi[q] > L.parts.lo[q + 2]) ok = false;
-            }
-            if (!ok) { lrep = l; break; }
-        }
-        H.lrep = lrep < 1 ? 1 : lrep;
-        if (trace) fprintf(stderr, "ssrs_potential_solve: rank %d of %d, levels %d, redundant from level %d\n", H.rank, H.nparts, nl, H.lrep);
+        if (H.lrep > nl - 1) H.lrep = nl - 1;       // the coarsest level is always redundant
+        if (H.lrep < 1) H.lrep = 1;
+        if (trace) fprintf(stderr, "ssrs_potential_solve: rank %d of %d, levels %d, redundant from level %d\n", H.rank, H.lv[0].parts.n, nl, H.lrep);
     }
     const double t_setup = now_ms();
 

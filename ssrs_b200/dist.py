@@ -33,6 +33,16 @@ def barrier() -> None:
         d.barrier()
 
 
+def agree(flag: bool) -> bool:
+    """Rank 0's value of `flag` on every rank (decisions that lead into a collective must not diverge)."""
+    d = _dist()
+    if not d:
+        return bool(flag)
+    box = [bool(flag)]
+    d.broadcast_object_list(box, src=0)
+    return bool(box[0])
+
+
 def shard_range(n: int, r: int, w: int):
     """Contiguous block [lo, hi) of global track ids owned by rank r of w (sizes differ by at most one)."""
     base, rem = divmod(int(n), int(w))

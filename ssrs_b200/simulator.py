@@ -196,6 +196,8 @@ class Simulator(Config):
         fname = self._get_potential_fname(case_id, real_id, self.mode_data_dir)
         id_str = self._get_id_string(case_id, real_id)
         try:
+            if not _dist.agree(os.path.exists(f'{fname}.npy')):
+                raise FileNotFoundError         # the solve is collective: all ranks follow rank 0's view of the cache
             potential = np.load(f'{fname}.npy')
             if potential.shape != self.gridsize:
                 raise FileNotFoundError
@@ -206,7 +208,8 @@ class Simulator(Config):
         except FileNotFoundError:
             t0 = time.time()
             print(f'{id_str}: Computing potential..', end="", flush=True)
-            pot_dev, stats = solve_potential_device(updraft, self.track_direction, strict=False)
+            pot_dev, stats = solve_potential_device(updraft, self.track_direction, strict=False,
+                                                    sharded=_dist.world_size() > 1)       # row-sharded over the ranks
             self.timings['potential_s'] = time.time() - t0
             self.solve_stats = stats
             print(f'took {_elapsed(t0)}', flush=True)
@@ -263,7 +266,7 @@ class Simulator(Config):
                                             self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
                                             fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
                                             record=record)
-                presence = _dist.allreduce_sum(res.presence)
+                presence = _dist.presence_allreduce(res.presence)        # ssrs_presence_allreduce (NCCL) when world > 1
                 steps = _dist.allreduce_sum(res._total.clone())
                 torch.cuda.synchronize()
                 self.timings['tracks_s'] = time.time() - t0
