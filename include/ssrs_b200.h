@@ -79,7 +79,8 @@ SSRS_API int ssrs_threshold(const float* in, float* out, int64_t n, float thresh
  * rtol: relative 2-norm residual of the un-normalised system; <= 0 (default) iterates to the accuracy float64 can
  *   attain (the solver estimates the residual floor d_i*ulp(phi_i)/2 and stops within it); max_iter <= 0 -> 300.
  * potential: float32 [rows][cols] out (the reference returns float32, :128).
- * Allocates its workspace internally (cudaMalloc) and frees it before returning; synchronous.
+ * Workspace (~300 B/cell) comes from a per-device arena of large cudaMalloc blocks that stays cached between
+ * solves (a seasonal run solves once per wind case); ssrs_release_workspace() returns it.  Synchronous.
  * Returns SSRS_ERR_NOT_CONVERGED (potential still written) if the tolerance was not reached.
  */
 typedef struct ssrs_solve_stats {
@@ -99,6 +100,9 @@ SSRS_API int ssrs_potential_solve(const float* conductivity, int rows, int cols,
                                   const int64_t* bnodes_host, const double* bvalues_host, int64_t n_bnodes,
                                   double rtol, int max_iter, float* potential, ssrs_solve_stats* stats,
                                   void* stream);
+
+/* Frees the solver's cached workspace on the current device (not while a solve is running). */
+SSRS_API int ssrs_release_workspace(void);
 
 /* Row-sharded solve (BASELINE config 5): the grid's rows are split into `comm->size` contiguous
  * slabs; rank r owns slab r.  Every rank passes the SAME full conductivity raster (fields are replicated for the

@@ -23,6 +23,7 @@ EXPORTS = {
                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_potential_solve_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                                C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_release_workspace": (C.c_int, []),
     "ssrs_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ssrs_comm_create_nccl": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ssrs_comm_destroy": (C.c_int, [C.c_void_p]),

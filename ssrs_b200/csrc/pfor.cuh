@@ -27,8 +27,14 @@ namespace par {
 #define SSRS_HD
 typedef void* stream_t;
 
-inline int dev_alloc(void** p, size_t bytes, stream_t) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : -1; }
-inline void dev_free(void* p, stream_t) { free(p); }
+// workspace arenas (see the CUDA build below); on the host every block is its own malloc
+struct Arena {
+    std::vector<void*> blocks;
+    size_t mark() const { return blocks.size(); }
+    void* alloc(size_t bytes) { void* p = malloc(bytes ? bytes : 1); if (p) blocks.push_back(p); return p; }
+    void release_to(size_t m) { while (blocks.size() > m) { free(blocks.back()); blocks.pop_back(); } }
+};
+inline Arena& arena(bool temp) { static thread_local Arena a[2]; return a[temp ? 1 : 0]; }
 inline int dev_zero(void* p, size_t bytes, stream_t) { memset(p, 0, bytes); return 0; }
 inline int dev_fill_byte(void* p, int v, size_t bytes, stream_t) { memset(p, v, bytes); return 0; }
 inline int copy_d2d(void* d, const void* s, size_t bytes, stream_t) { memcpy(d, s, bytes); return 0; }
@@ -77,10 +83,61 @@ inline void atomic_max_i64(int64_t* p, int64_t v) { if (v > *p) *p = v; }
 #define SSRS_HD __host__ __device__
 typedef cudaStream_t stream_t;
 
-// stream-ordered allocation from the device's default memory pool: freed blocks stay cached in the pool
-// (release threshold raised in potential.cu), so repeated solves do not pay cudaMalloc/cudaFree
-inline int dev_alloc(void** p, size_t bytes, cudaStream_t s) { return cudaMallocAsync(p, bytes ? bytes : 1, s) == cudaSuccess ? 0 : -1; }
-inline void dev_free(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+// Workspace arenas.  The solver needs ~300 B/cell (9 GB at 5000 x 6000) in ~150 blocks per solve.  Measured on
+// B200: cudaMallocAsync from the default pool re-maps physical memory on most solves (setup 50 ms .. 4.7 s for
+// the same grid), so the workspace is bump-allocated from a few large cudaMalloc chunks that stay cached per
+// device between solves (one arena for blocks that live until the solve returns, one used as a stack for
+// scoped temporaries); ssrs_release_workspace() returns them to the driver.
+struct Arena {
+    struct Chunk { char* base; size_t size, used; };
+    std::vector<Chunk> chunks;
+    int device = -1;
+    static constexpr size_t ALIGN = 512, MIN_CHUNK = (size_t)256 << 20;
+    // a mark encodes (chunk index, offset); allocation is strictly stack-like
+    struct Mark { size_t chunk, used; };
+    Mark mark() const { return chunks.empty() ? Mark{0, 0} : Mark{chunks.size() - 1, chunks.back().used}; }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + ALIGN - 1) / ALIGN * ALIGN;
+        if (bytes == 0) bytes = ALIGN;
+        if (!chunks.empty() && chunks.back().size - chunks.back().used >= bytes) {
+            void* p = chunks.back().base + chunks.back().used;
+            chunks.back().used += bytes;
+            return p;
+        }
+        size_t want = bytes > MIN_CHUNK ? bytes : MIN_CHUNK;
+        if (!chunks.empty() && chunks.back().size > want) want = chunks.back().size;   // grow geometrically-ish
+        void* base = nullptr;
+        if (cudaMalloc(&base, want) != cudaSuccess) {
+            cudaGetLastError();
+            if (want == bytes || cudaMalloc(&base, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            want = bytes;
+        }
+        chunks.push_back(Chunk{(char*)base, want, bytes});
+        return base;
+    }
+    void release_to(Mark m) {
+        if (chunks.empty()) return;
+        for (size_t k = m.chunk + 1; k < chunks.size(); ++k) chunks[k].used = 0;
+        if (m.chunk < chunks.size()) chunks[m.chunk].used = m.used;
+    }
+    size_t capacity() const { size_t t = 0; for (const Chunk& c : chunks) t += c.size; return t; }
+    bool idle() const { for (const Chunk& c : chunks) if (c.used) return false; return true; }
+    void free_all() { for (Chunk& c : chunks) cudaFree(c.base); chunks.clear(); }
+    // one chunk of at least `bytes` before a solve starts (no-op when the cached capacity already suffices)
+    void reserve(size_t bytes) {
+        if (!idle()) return;
+        if (chunks.size() == 1 && chunks[0].size >= bytes) return;
+        const size_t have = capacity();
+        if (chunks.size() > 1 || have < bytes) {
+            free_all();
+            void* base = nullptr;
+            const size_t want = have > bytes ? have : bytes;
+            if (cudaMalloc(&base, want) == cudaSuccess) chunks.push_back(Chunk{(char*)base, want, 0});
+            else cudaGetLastError();        // fall back to growing on demand
+        }
+    }
+};
+Arena& arena(bool temp);      // per device and host thread (defined in potential.cu)
 inline int dev_zero(void* p, size_t bytes, stream_t s) { return cudaMemsetAsync(p, 0, bytes, s) == cudaSuccess ? 0 : -1; }
 inline int dev_fill_byte(void* p, int v, size_t bytes, stream_t s) { return cudaMemsetAsync(p, v, bytes, s) == cudaSuccess ? 0 : -1; }
 inline int copy_d2d(void* d, const void* s, size_t b, stream_t st) { return cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : -1; }
@@ -210,12 +267,14 @@ inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t
     if (cudaMemcpyAsync(&last_in, data + n - 1, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
     size_t tmp_bytes = 0;
     if (cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, data, data, n, s) != cudaSuccess) return -1;
-    void* tmp = nullptr;
-    if (cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s) != cudaSuccess) return -1;
+    Arena& ar = arena(true);
+    const Arena::Mark mk = ar.mark();
+    void* tmp = ar.alloc(tmp_bytes ? tmp_bytes : 1);
+    if (!tmp) return -1;
     cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, data, data, n, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_out, data + n - 1, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFreeAsync(tmp, s);
+    ar.release_to(mk);
     if (e != cudaSuccess) return -1;
     *total = last_in + last_out;
     return 0;

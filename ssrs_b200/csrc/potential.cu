@@ -44,6 +44,13 @@ void set_error(const char* fmt, ...) {
 int sm_count();
 namespace par {
 int grid_cap() { return sm_count() * 8; }
+Arena& arena(bool temp) {
+    static thread_local Arena a[64][2];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    return a[dev][temp ? 1 : 0];
+}
 double* reduce_scratch() {   // small persistent buffer (plain cudaMalloc, lives for the process)
     static thread_local double* buf = nullptr;
     static thread_local int dev_of = -1;
@@ -209,23 +216,24 @@ SSRS_HD inline double fine_apply64(const FineGraph& g, const FineWeights& W, int
 }
 
 // ---- storage ------------------------------------------------------------------------------------
+// Blocks of one scope, bump-allocated from a workspace arena (pfor.cuh) and handed back together when the scope
+// ends: `temp` pools are scoped temporaries (stack discipline), the other pool lives as long as the solve.
 struct Pool {
-    std::vector<void*> ptrs;
+    Arena& ar;
+#ifdef SSRS_HOST_EMU
+    size_t mk;
+#else
+    Arena::Mark mk;
+#endif
     size_t bytes = 0;
-    stream_t st;
-    explicit Pool(stream_t s) : st(s) {}
+    explicit Pool(stream_t, bool temp = false) : ar(arena(temp)), mk(ar.mark()) {}
     template <class T> T* get(i64 count) {
-        void* p = nullptr;
-        if (dev_alloc(&p, sizeof(T) * (size_t)(count > 0 ? count : 1), st) != 0) return nullptr;
-        ptrs.push_back(p);
-        bytes += sizeof(T) * (size_t)count;
+        void* p = ar.alloc(sizeof(T) * (size_t)(count > 0 ? count : 1));
+        if (p) bytes += sizeof(T) * (size_t)count;
         return static_cast<T*>(p);
     }
-    void release(void* p) {
-        for (size_t k = 0; k < ptrs.size(); ++k)
-            if (ptrs[k] == p) { dev_free(p, st); ptrs.erase(ptrs.begin() + k); return; }
-    }
-    ~Pool() { for (void* p : ptrs) dev_free(p, st); }
+    void release(void*) {}          // reclaimed with the pool
+    ~Pool() { ar.release_to(mk); }
 };
 
 struct Level {
@@ -248,7 +256,7 @@ template <class G>
 int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_rounds, Parts* next, stream_t st) {
     const i64 n = g.size();
     float* rowmax; int *mate, *best, *root, *root2;
-    Pool tmp(st);
+    Pool tmp(st, true);
     rowmax = tmp.get<float>(n); mate = tmp.get<int>(n); best = tmp.get<int>(n); root = tmp.get<int>(n); root2 = tmp.get<int>(n);
     if (!rowmax || !mate || !best || !root || !root2) { set_error("ssrs_potential_solve: out of device memory in coarsen"); return SSRS_ERR_CUDA; }
     const float th = (float)theta;
@@ -378,7 +386,7 @@ template <class G>
 int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
     const i64 nc = L.nc;
     const int* agg = L.agg; const i64* memptr = L.memptr; const int* mem = L.mem;
-    Pool tmp(st);
+    Pool tmp(st, true);
     i64* off = tmp.get<i64>(nc + 1);
     int* len = tmp.get<int>(nc);
     if (!off || !len) { set_error("ssrs_potential_solve: out of device memory in galerkin"); return SSRS_ERR_CUDA; }
@@ -669,7 +677,7 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
     const Parts P = L.parts;
     for (int q = 0; q < P.n; ++q) { L.ref_lo[q] = P.lo[q]; L.ref_hi[q] = P.lo[q + 1]; }
     if (P.n > 1) {
-        Pool tmp(st);
+        Pool tmp(st, true);
         i64* ref = tmp.get<i64>(2 * P.n);
         if (!ref) { set_error("ssrs_potential_solve: out of device memory in build_ell"); return SSRS_ERR_CUDA; }
         i64 init[2 * SSRS_MAX_RANKS];
@@ -803,7 +811,7 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
 int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
     const i64 n = C.n;
     double *D, *I, *colk, *rowD, *rowI;
-    Pool tmp(st);
+    Pool tmp(st, true);
     D = tmp.get<double>(n * n); colk = tmp.get<double>(n); rowD = tmp.get<double>(n); rowI = tmp.get<double>(n);
     AMG_ALLOC(I, double, n * n);
     if (!D || !colk || !rowD || !rowI) { set_error("ssrs_potential_solve: out of device memory in dense_inverse"); return SSRS_ERR_CUDA; }
@@ -897,13 +905,9 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     const double t_begin = now_ms();
     const bool trace = getenv("SSRS_SOLVE_TRACE") != nullptr;      // per-iteration residuals on stderr
 #ifndef SSRS_HOST_EMU
-    {   // keep freed workspace cached in the device's default pool between solves
-        int dev = 0; cudaMemPool_t mp;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
-            uint64_t thresh = ~0ULL;
-            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thresh);
-        }
-    }
+    // measured: 304 B/cell live until the solve returns, ~150 B/cell of scoped temporaries (Galerkin scratch)
+    arena(false).reserve((size_t)n * 330 + ((size_t)64 << 20));
+    arena(true).reserve((size_t)n * 170 + ((size_t)64 << 20));
 #endif
     Pool pool(st);
     Hierarchy H;
@@ -1190,6 +1194,15 @@ int SOLVE_NAME(const float* K, int rows, int cols, const int64_t* bnodes_host, c
                int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats, void* stream) {
     return ssrs::amg::solve_impl(K, rows, cols, bnodes_host, bvalues_host, n_bnodes, rtol, max_iter, phi, stats, nullptr, stream);
 }
+#ifndef SSRS_HOST_EMU
+extern "C" __attribute__((visibility("default")))
+int ssrs_release_workspace(void) {
+    if (!ssrs::par::arena(false).idle() || !ssrs::par::arena(true).idle()) { set_error("ssrs_release_workspace: a solve is in progress"); return SSRS_ERR_INVALID; }
+    ssrs::par::arena(false).free_all();
+    ssrs::par::arena(true).free_all();
+    return SSRS_OK;
+}
+#endif
 extern "C" __attribute__((visibility("default")))
 int SOLVE_SHARDED_NAME(const float* K, int rows, int cols, const int64_t* bnodes_host, const double* bvalues_host,
                        int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats,
