@@ -200,6 +200,28 @@ SSRS_API int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const i
 SSRS_API int ssrs_smooth_presence(const long long* row_prefix, int rows, int cols, int radius, float* out,
                                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" rows: the producers in front of stage 1.
+ *
+ * ssrs_interp_wind replaces Simulator._get_interpolated_wind_conditions / _interpolate_wtk_vardata
+ * (ssrs/simulator.py:765-792, scipy griddata(method='linear') on the u/v components): px/py/east/north are
+ * float64 [npoints] (projected site coordinates; east = speed*sin(dirn), north = speed*cos(dirn), :784-785),
+ * triangles int32 [ntriangles][3] is the Delaunay triangulation of the sites (host: scipy.spatial.Delaunay, the
+ * same Qhull griddata uses).  Cell (r, c) sits at (x0 + c*resolution, y0 + r*resolution) (get_terrain_grid,
+ * :177-185).  owner_scratch: int32 [rows][cols].  Outputs float32 [rows][cols]; NaN outside the convex hull. */
+SSRS_API int ssrs_interp_wind(const double* px, const double* py, const double* east, const double* north, int npoints,
+                              const int32_t* triangles, int ntriangles, double x0, double y0, double resolution,
+                              int rows, int cols, int32_t* owner_scratch, float* wspeed, float* wdirn, void* stream);
+
+/* compute_thermals (ssrs/layers.py:188-214) in two steps: the random seeds (Philox4x32-10 keyed by (seed, cell):
+ * same distribution as the reference's np.random draws, not the same stream) and the deterministic
+ * scipy.ndimage.gaussian_filter(sigma, mode='constant', truncate) smoothing.  tmp: float32 [rows][cols];
+ * weights_scratch: float32 [2*int(truncate*sigma+0.5)+1] on the device. */
+SSRS_API int ssrs_thermal_seeds(const float* aspect, int rows, int cols, float thermal_intensity_scale, uint64_t seed,
+                                float* seeds, void* stream);
+SSRS_API int ssrs_gaussian_blur(const float* in, float* out, float* tmp, int rows, int cols, float sigma, float truncate,
+                                float* weights_scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,31 @@ def main():
     for rad in (2, 5):
         sm[f"smooth_{rad}"] = M.compute_smooth_presence_counts(trajs, U.shape, rad)
     np.savez_compressed(os.path.join(OUT, "smooth.npz"), **sm)
+    # ---- "next" rows f-2 / f-3: wind interpolation and thermals --------------------------------------
+    from oracle import oracle_np as O
+    wn = {}
+    rows, cols, res = 70, 90, 250.0
+    xl, yl, spd, drn = synthetic_wind_lattice(rows, cols, res, spacing_m=2000.0, seed=7)
+    xg = np.linspace(0.0, (cols - 1) * res, cols)                   # get_terrain_grid, simulator.py:177-185
+    yg = np.linspace(0.0, (rows - 1) * res, rows)
+    ws, wd = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg)            # scipy griddata, as the reference calls it
+    wn.update(dict(a_x=xl, a_y=yl, a_speed=spd, a_dirn=drn, a_shape=np.array([rows, cols]), a_res=res, a_ws=ws, a_wd=wd))
+    # sites that do not cover the grid: NaN outside the hull; wrap-around directions near north
+    rng = np.random.RandomState(12)
+    xb = rng.uniform(2000, 18000, 40); yb = rng.uniform(1000, 15000, 40)
+    sb = rng.uniform(3, 14, 40); db = np.mod(rng.normal(0.0, 40.0, 40), 360.0)
+    ws2, wd2 = O.interpolated_wind_conditions(xb, yb, sb, db, xg, yg)
+    wn.update(dict(b_x=xb, b_y=yb, b_speed=sb, b_dirn=db, b_ws=ws2, b_wd=wd2))
+    # thermals: the reference function itself (layers.py:188-214) for distribution statistics, and its smoothing
+    z = synthetic_dem(80, 100, 100.0, seed=11, rough_rms=8.0)
+    asp = L.compute_aspect_degrees(z.astype(np.float64), 100.0)
+    np.random.seed(3)
+    reals = np.stack([L.compute_thermals(asp, 2.0) for _ in range(40)])
+    rng = np.random.RandomState(8)
+    seeds = np.where(rng.rand(80, 100) < 0.01, rng.lognormal(5.0, 0.5, (80, 100)), 0.0)
+    wn.update(dict(t_aspect=asp.astype(np.float32), t_reference_means=reals.mean(axis=(1, 2)), t_reference_max=reals.max(axis=(1, 2)),
+                   t_seeds=seeds.astype(np.float32), t_smoothed=O.smooth_thermals(seeds.astype(np.float32).astype(np.float64))))
+    np.savez_compressed(os.path.join(OUT, "wind_thermals.npz"), **wn)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -387,3 +387,38 @@ def smooth_presence(counts: np.ndarray, radius: float) -> np.ndarray:
     kernel[x ** 2 + y ** 2 <= krad ** 2] = 1
     kernel /= np.sum(kernel)
     return ssg.convolve2d(counts, kernel, mode="same").astype(np.float32)
+
+
+# ---- "next" rows f-2 / f-3 ------------------------------------------------------------
+def interpolated_wind_conditions(xlocs, ylocs, wspeed, wdirn, xgrid, ygrid, method: str = 'linear'):
+    """ssrs/simulator.py:765-792 (`_interpolate_wtk_vardata` + `_get_interpolated_wind_conditions`): u/v components
+    through scipy.interpolate.griddata — the third-party arithmetic the reference itself calls — then speed and
+    direction.  float64 [len(ygrid), len(xgrid)], NaN outside the convex hull of the sites."""
+    from scipy.interpolate import griddata
+    points = np.array([xlocs, ylocs]).T                                  # :770
+    xmesh, ymesh = np.meshgrid(xgrid, ygrid)                             # :771
+    easterly = np.multiply(wspeed, np.sin(np.asarray(wdirn) * np.pi / 180.))     # :784
+    northerly = np.multiply(wspeed, np.cos(np.asarray(wdirn) * np.pi / 180.))    # :785
+    ie = griddata(points, easterly, (xmesh, ymesh), method=method)       # :772-773
+    inn = griddata(points, northerly, (xmesh, ymesh), method=method)
+    ws = np.sqrt(np.square(ie) + np.square(inn))                         # :788-789
+    wd = np.arctan2(ie, inn)                                             # :790
+    wd = np.mod(wd + 2. * np.pi, 2. * np.pi)                             # :791
+    return ws, wd * 180. / np.pi
+
+
+def thermal_hit_probability(aspect: np.ndarray) -> np.ndarray:
+    """ssrs/layers.py:194-202: probability that a cell seeds a thermal: inside the 10 % border,
+    np.random.randint(1, int(wtfactor)) == 5 with wtfactor = 1000 + |aspect - 180| / 180 * 2000."""
+    ysize, xsize = aspect.shape
+    bx, by = int(0.1 * xsize), int(0.1 * ysize)
+    p = np.zeros(aspect.shape)
+    wt = (1000 + (np.abs(aspect - 180.) / 180.) * 2000.).astype(np.int64)        # int(wtfactor)
+    p[by:ysize - by, bx:xsize - bx] = 1.0 / (wt[by:ysize - by, bx:xsize - bx] - 1)
+    return p
+
+
+def smooth_thermals(wt_init: np.ndarray) -> np.ndarray:
+    """ssrs/layers.py:211: scipy.ndimage.gaussian_filter(wt_init, sigma=4, mode='constant')."""
+    from scipy import ndimage
+    return ndimage.gaussian_filter(wt_init, sigma=4, mode='constant')

@@ -23,6 +23,11 @@ EXPORTS = {
                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_potential_solve_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                                C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_interp_wind": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_thermal_seeds": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "ssrs_gaussian_blur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p]),
     "ssrs_release_workspace": (C.c_int, []),
     "ssrs_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ssrs_comm_create_nccl": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -5,7 +5,9 @@ Same names and argument meaning as the reference (`/root/reference/ssrs/layers.p
   compute_aspect_degrees(z_mat, res)                     :96-128
   compute_orographic_updraft(wspeed, wdirn, slope, aspect, min_updraft_val=0.)   :11-22
   get_above_threshold_speed(in_array, threshold)         :171-185
-plus `updraft_fields`, the fused form the Simulator uses (one kernel, one pass over the DEM).
+  compute_thermals(aspect, thermal_intensity_scale)      :188-214   (distributional parity: own RNG stream)
+plus `interpolate_wind_to_grid` (the reference's `Simulator._get_interpolated_wind_conditions`,
+`ssrs/simulator.py:765-792`), `gaussian_filter_constant` and `updraft_fields`, the fused form the Simulator uses (one kernel, one pass over the DEM).
 Inputs may be numpy arrays (copied to the GPU and back, results as numpy) or CUDA torch tensors
 (results stay on the device).  Arithmetic is float32 on the device (the reference computes in float64
 and stores float32, `ssrs/simulator.py:198`); agreement is within 1e-5 of each field's maximum.
@@ -85,3 +87,79 @@ def get_above_threshold_speed(in_array, threshold: float):
     out = torch.empty_like(x)
     N.check(lib.ssrs_threshold(N.ptr(x), N.ptr(out), x.numel(), float(threshold), N.current_stream()), "ssrs_threshold")
     return _back(out, was_tensor)
+
+
+def gaussian_filter_constant(in_array, sigma: float = 4.0, truncate: float = 4.0):
+    """scipy.ndimage.gaussian_filter(in_array, sigma, mode='constant', truncate=truncate) on the GPU (float32)."""
+    torch = N.require_cuda()
+    lib = N.load()
+    x, was_tensor = _to_device(in_array, torch)
+    if x.dim() != 2:
+        raise ValueError("gaussian_filter_constant expects a 2-D raster")
+    rows, cols = x.shape
+    out, tmp = torch.empty_like(x), torch.empty_like(x)
+    w = torch.empty(2 * int(truncate * sigma + 0.5) + 1, dtype=torch.float32, device="cuda")
+    N.check(lib.ssrs_gaussian_blur(N.ptr(x), N.ptr(out), N.ptr(tmp), rows, cols, float(sigma), float(truncate), N.ptr(w),
+                                   N.current_stream()), "ssrs_gaussian_blur")
+    return _back(out, was_tensor)
+
+
+def thermal_seeds(aspect, thermal_intensity_scale: float, seed: int):
+    """The un-smoothed seed field of `compute_thermals` (reference `layers.py:192-206`), Philox keyed by (seed, cell)."""
+    torch = N.require_cuda()
+    lib = N.load()
+    a, was_tensor = _to_device(aspect, torch)
+    rows, cols = a.shape
+    out = torch.empty_like(a)
+    N.check(lib.ssrs_thermal_seeds(N.ptr(a), rows, cols, float(thermal_intensity_scale), int(seed) & (2 ** 64 - 1),
+                                   N.ptr(out), N.current_stream()), "ssrs_thermal_seeds")
+    return _back(out, was_tensor)
+
+
+def compute_thermals(aspect, thermal_intensity_scale: float, seed=None):
+    """Reference `layers.py:188-214`: smoothed random thermals.  The reference consumes numpy's global stream cell
+    by cell; here `seed` (default: one draw from numpy's global stream, so `np.random.seed` still controls it)
+    keys a counter-based generator — same distribution, different realisation."""
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    torch = N.require_cuda()
+    a, was_tensor = _to_device(aspect, torch)
+    wt = gaussian_filter_constant(thermal_seeds(a, thermal_intensity_scale, seed), 4.0, 4.0)      # :211
+    return _back(wt, was_tensor)
+
+
+def delaunay_triangles(xlocs, ylocs):
+    """Qhull Delaunay triangulation of the wind sites — what scipy's griddata(method='linear') builds internally."""
+    from scipy.spatial import Delaunay
+    pts = np.stack([np.asarray(xlocs, dtype=np.float64), np.asarray(ylocs, dtype=np.float64)], 1)
+    return np.ascontiguousarray(Delaunay(pts).simplices, dtype=np.int32)
+
+
+def interpolate_wind_to_grid(xlocs, ylocs, wspeed, wdirn, x0: float, y0: float, res: float, gridsize,
+                             triangles=None, method: str = 'linear'):
+    """Reference `Simulator._get_interpolated_wind_conditions` (`simulator.py:778-792`): wind speed/direction at
+    scattered sites -> CUDA float32 rasters `[rows, cols]` (speed, direction in degrees), NaN outside the sites'
+    convex hull.  `triangles` may be passed to reuse one triangulation for many wind cases."""
+    if method != 'linear':
+        raise NotImplementedError(f"wtk_interp_type={method!r}: only 'linear' (the Config default) runs on the GPU")
+    torch = N.require_cuda()
+    lib = N.load()
+    x = np.ascontiguousarray(xlocs, dtype=np.float64)
+    y = np.ascontiguousarray(ylocs, dtype=np.float64)
+    ws = np.asarray(wspeed, dtype=np.float64)
+    wd = np.asarray(wdirn, dtype=np.float64)
+    if not (x.shape == y.shape == ws.shape == wd.shape) or x.ndim != 1 or x.size < 3:
+        raise ValueError("site coordinates and wind values must be 1-D arrays of equal length (>= 3 sites)")
+    east = np.multiply(ws, np.sin(wd * np.pi / 180.))               # simulator.py:784-785
+    north = np.multiply(ws, np.cos(wd * np.pi / 180.))
+    tri = delaunay_triangles(x, y) if triangles is None else np.ascontiguousarray(triangles, dtype=np.int32)
+    rows, cols = int(gridsize[0]), int(gridsize[1])
+    dev = lambda a: torch.from_numpy(a).to("cuda")
+    dx, dy, de, dn, dt = dev(x), dev(y), dev(east), dev(north), dev(tri)
+    owner = torch.empty((rows, cols), dtype=torch.int32, device="cuda")
+    out_s = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+    out_d = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+    N.check(lib.ssrs_interp_wind(N.ptr(dx), N.ptr(dy), N.ptr(de), N.ptr(dn), x.size, N.ptr(dt), tri.shape[0], float(x0),
+                                 float(y0), float(res), rows, cols, N.ptr(owner), N.ptr(out_s), N.ptr(out_d),
+                                 N.current_stream()), "ssrs_interp_wind")
+    return out_s, out_d

@@ -7,6 +7,8 @@ names, case/ID strings and on-disk artefacts (`<case>_orograph.npy` f32, `<id>_p
     reference                                           here
     compute_orographic_updraft_uniform   :189-198       one fused stencil kernel (ssrs_updraft)
     compute_orographic_updrafts_using_wtk :200-215      same kernel with per-cell wind rasters
+    _get_interpolated_wind_conditions    :765-792       barycentric interpolation kernel (ssrs_interp_wind)
+    compute_thermal_updrafts             :217-228       Philox seeds + separable Gaussian blur on the GPU
     load_updrafts                        :230-243       threshold on the GPU (ssrs_threshold)
     get_directional_potential            :259-288       matrix-free AMG/BiCGStab solve (ssrs_potential_solve)
     simulate_tracks                      :332-386       one batched launch (ssrs_step_tracks) instead of mp.Pool
@@ -15,7 +17,10 @@ names, case/ID strings and on-disk artefacts (`<case>_orograph.npy` f32, `<id>_p
 Out of scope: terrain/WTK/turbine downloads, CRS handling and matplotlib plotting.  The reference
 constructor always downloads terrain; here it is injected with keyword-only extensions:
     elevation=   float raster [rows=north, cols=east] matching `gridsize`
-    wind_cases=  {case_id: (wspeed, wdirn)} rasters or scalars for snapshot/seasonal modes (stands in for WTK)
+    wind_cases=  {case_id: (wspeed, wdirn)} for snapshot/seasonal modes (stands in for the WTK download): rasters
+                 [rows, cols], scalars, or — with wind_points= — 1-D values at the scattered sites, which are then
+                 interpolated to the terrain grid on the GPU like the reference's griddata(linear) recipe
+    wind_points= (xlocs, ylocs) projected site coordinates (the reference's get_wtk_locs())
     bounds=      projected bounds (west, south, east, north); default puts the south-west corner at (0, 0)
 When `torch.distributed` is initialised, tracks are block-partitioned by global id over the ranks, fields are
 replicated and presence maps are summed with one all-reduce (NCCL on GPUs).
@@ -53,7 +58,7 @@ class Simulator(Config):
     time_format = 'y%Ym%md%dh%H'
 
     def __init__(self, in_config: Config = None, *, elevation=None, wind_cases: Optional[Dict] = None,
-                 bounds=None, **kwargs) -> None:
+                 wind_points=None, bounds=None, **kwargs) -> None:
         if in_config is None:
             super().__init__(**kwargs)
         else:
@@ -110,6 +115,11 @@ class Simulator(Config):
                 raise ValueError(f"sim_mode={self.sim_mode!r} needs wind_cases= (WTK download is outside the hot path)")
             self.case_ids = list(wind_cases.keys())
             self._wind_cases = wind_cases
+            self._wind_points = None
+            if wind_points is not None:
+                from .layers import delaunay_triangles
+                xl, yl = (np.asarray(v, dtype=np.float64) for v in wind_points)
+                self._wind_points = (xl, yl, delaunay_triangles(xl, yl))       # one triangulation for all cases
             self.compute_orographic_updrafts_using_wtk()
         else:
             print(f'Uniform mode: Wind speed = {self.uniform_windspeed} m/s')
@@ -161,26 +171,49 @@ class Simulator(Config):
         t0 = time.time()
         for case_id in self.case_ids:
             ws, wd = self._wind_cases[case_id]
+            if self._wind_points is not None and np.ndim(ws) == 1:
+                ws, wd = self._get_interpolated_wind_conditions(ws, wd)
             out = updraft_fields(self._elev, self.resolution, ws, wd, self.updraft_threshold, want=("orograph",))
             self._save_orograph(case_id, out["orograph"])
         print(f'took {_elapsed(t0)}', flush=True)
 
+    def _get_interpolated_wind_conditions(self, wspeed, wdirn):
+        """Reference :778-792 — site values -> CUDA rasters (speed, direction in degrees) on the terrain grid."""
+        from .layers import interpolate_wind_to_grid
+        xl, yl, tri = self._wind_points
+        return interpolate_wind_to_grid(xl, yl, wspeed, wdirn, self.bounds[0], self.bounds[1], self.resolution,
+                                        self.gridsize, triangles=tri, method=self.wtk_interp_type)
+
     def compute_thermal_updrafts(self, case_id: str):
+        """Reference :217-228.  Realisation r is keyed by (sim_seed, case, r): reproducible for sim_seed >= 0."""
         if self.thermals_realization_count > 0:
-            raise NotImplementedError("thermal realisations are outside the B200 hot path (SURVEY.md §8f-3)")
-        print('No thermals requested!', flush=True)
+            from .layers import compute_thermals
+            print('Computing thermal updrafts...', flush=True)
+            aspect = updraft_fields(self._elev, self.resolution, 0.0, 0.0, want=("aspect",))["aspect"]
+            ci = self.case_ids.index(case_id)
+            for real_id in range(self.thermals_realization_count):
+                seed = None if self.sim_seed < 0 else (self.sim_seed * 7919 + ci * 104729 + real_id + 1)
+                thermals = compute_thermals(aspect, 2.0, seed=seed)
+                if _dist.rank() == 0:
+                    np.save(f'{self._get_thermal_fname(case_id, real_id, self.mode_data_dir)}.npy', thermals.cpu().numpy())
+            _dist.barrier()
+        else:
+            print('No thermals requested!', flush=True)
 
     def load_updrafts(self, case_id: str, apply_threshold=True):
-        """List with the (thresholded) orographic updraft, float32 numpy (reference :230-243)."""
-        oro = np.load(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy')
-        if apply_threshold:
-            return [get_above_threshold_speed(oro, self.updraft_threshold)]
-        return [oro]
+        """[orograph, orograph + thermals_0, ...] (thresholded), float32 numpy (reference :230-243)."""
+        return [u.cpu().numpy() for u in self._load_updrafts_device(case_id, apply_threshold)]
 
-    def _load_updraft_device(self, case_id):
+    def _load_updrafts_device(self, case_id, apply_threshold=True):
         torch = N.require_cuda()
         oro = torch.from_numpy(np.load(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy')).to("cuda")
-        return get_above_threshold_speed(oro, self.updraft_threshold)
+        updrafts = [oro]
+        for real_id in range(int(self.thermals_realization_count)):
+            th = np.load(f'{self._get_thermal_fname(case_id, real_id, self.mode_data_dir)}.npy')
+            updrafts.append(oro + torch.from_numpy(th).to("cuda"))
+        if apply_threshold:
+            updrafts = [get_above_threshold_speed(u, self.updraft_threshold) for u in updrafts]
+        return updrafts
 
     def _get_orograph_fname(self, case_id: str, dirname: str = './'):
         return os.path.join(dirname, f'{case_id}_orograph')
@@ -249,8 +282,7 @@ class Simulator(Config):
         lo, hi = _dist.shard_range(n, _dist.rank(), _dist.world_size())
         record = (n <= TRACKS_PKL_LIMIT) if save_tracks is None else bool(save_tracks)
         for ci, case_id in enumerate(self.case_ids):
-            updraft = self._load_updraft_device(case_id)
-            for real_id in range(1):
+            for real_id, updraft in enumerate(self._load_updrafts_device(case_id)):
                 if self.sim_seed > 0:
                     np.random.seed(self.sim_seed + real_id)              # reference :351-352
                 id_str = self._get_id_string(case_id, real_id)
@@ -302,7 +334,7 @@ class Simulator(Config):
         summary = None
         for case_id in self.case_ids:
             case_prob = None
-            for real_id in range(1):
+            for real_id in range(1 + int(self.thermals_realization_count)):
                 counts = self._presence[self._get_id_string(case_id, real_id)]
                 pr = smooth_presence_counts(counts, int(round(krad)))
                 pr = pr / pr.max()

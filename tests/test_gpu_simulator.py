@@ -111,3 +111,39 @@ def test_smoothing_full_radius():
     inner = np.zeros_like(cnt); inner[300:400, 400:500] = cnt[300:400, 400:500]
     o2 = smooth_presence_counts(inner, 100)
     assert abs(o2.sum() - inner.sum()) <= 1e-3 * inner.sum()
+
+
+def test_snapshot_mode_wind_sites_and_thermals(tmp_path):
+    """BASELINE config 4 in miniature: wind given at scattered sites (a jittered 2 km lattice), interpolated to the
+    terrain grid on the GPU (reference simulator.py:765-792), plus one thermal realisation (layers.py:188-214,
+    simulator.py:217-243): realisation ids r0 (orographic only) and r1 (orographic + thermals)."""
+    from ssrs_b200 import Config, Simulator
+    from ssrs_b200.synth import synthetic_dem, synthetic_wind_lattice
+    rows, cols, res = 120, 160, 100.0
+    z = synthetic_dem(rows, cols, res, seed=4)
+    xl, yl, spd, drn = synthetic_wind_lattice(rows, cols, res, spacing_m=2000.0, seed=7)
+    cfg = Config(run_name="snap2", out_dir=str(tmp_path), sim_seed=3, sim_mode="snapshot", region_width_km=(16., 12.),
+                 resolution=res, track_count=64, track_start_region=(2, 14, 0.5, 1), track_direction=0.,
+                 thermals_realization_count=1)
+    sim = Simulator(cfg, elevation=z, wind_points=(xl, yl), wind_cases={"y2014m12d01h15": (spd, drn)})
+    data = sim.mode_data_dir
+    xg, yg = sim.get_terrain_grid()
+    ws_ref, wd_ref = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg)
+    _, _, oro_ref, _ = O.updraft_pipeline(z, res, ws_ref, wd_ref, 0.75)
+    oro = np.load(os.path.join(data, "y2014m12d01h15_orograph.npy"))
+    assert np.abs(oro - oro_ref).max() <= 1e-5 * oro_ref.max()
+    th = np.load(os.path.join(data, "y2014m12d01h15_r0_thermals.npy"))
+    assert th.dtype == np.float32 and th.shape == (rows, cols) and th.min() >= 0 and th.max() > 0
+    ups = sim.load_updrafts("y2014m12d01h15")
+    assert len(ups) == 2 and np.abs(ups[1] - O.get_above_threshold_speed(oro + th, 0.75)).max() <= 1e-5 * ups[1].max()
+    sim.simulate_tracks()
+    for r in (0, 1):
+        assert os.path.exists(os.path.join(data, f"y2014m12d01h15_d0_t75_fluidflow_r{r}_tracks.pkl"))
+        assert os.path.exists(os.path.join(data, f"y2014m12d01h15_d0_t75_fluidflow_r{r}_potential.npy"))
+    assert not np.array_equal(sim.presence_counts(real_id=0), sim.presence_counts(real_id=1))
+    summ = sim.plot_presence_map(radius=500.)
+    assert summ.max() == 1.0
+    # same seed -> the same thermal realisation (counter-based RNG keyed by sim_seed, case, realisation)
+    sim2 = Simulator(cfg.__class__(**{**cfg.__dict__, "run_name": "snap3"}), elevation=z, wind_points=(xl, yl),
+                     wind_cases={"y2014m12d01h15": (spd, drn)})
+    assert np.array_equal(np.load(os.path.join(sim2.mode_data_dir, "y2014m12d01h15_r0_thermals.npy")), th)

@@ -1,0 +1,113 @@
+"""Rows f-2 / f-3 of SURVEY.md §8f: wind interpolation (`ssrs/simulator.py:765-792`) and thermals
+(`ssrs/layers.py:188-214`).  CPU part: the oracle against the committed fixtures (tests/golden/wind_thermals.npz,
+written by oracle/make_golden.py with scipy's griddata — the routine the reference calls — and the reference's own
+compute_thermals).  GPU part: the CUDA kernels through the C-ABI against the same fixtures."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+
+LOGN_MEAN = float(np.exp(5.0 + 0.5 * 0.5 ** 2))          # E[lognormal(2 + 3, 0.5)], layers.py:203-204
+
+
+def _grid(g):
+    rows, cols = (int(v) for v in g["a_shape"])
+    res = float(g["a_res"])
+    return rows, cols, res, np.linspace(0.0, (cols - 1) * res, cols), np.linspace(0.0, (rows - 1) * res, rows)
+
+
+def test_oracle_wind_interpolation_matches_fixture(golden):
+    g = golden("wind_thermals")
+    rows, cols, res, xg, yg = _grid(g)
+    for k in "ab":
+        ws, wd = O.interpolated_wind_conditions(g[f"{k}_x"], g[f"{k}_y"], g[f"{k}_speed"], g[f"{k}_dirn"], xg, yg)
+        assert np.array_equal(np.isnan(ws), np.isnan(g[f"{k}_ws"]))
+        assert np.allclose(ws, g[f"{k}_ws"], rtol=1e-12, atol=1e-12, equal_nan=True)
+        assert np.allclose(wd, g[f"{k}_wd"], rtol=1e-12, atol=1e-9, equal_nan=True)
+    assert not np.isnan(g["a_ws"]).any() and np.isnan(g["b_ws"]).any()       # case b leaves the hull
+
+
+def test_oracle_thermal_statistics_match_reference(golden):
+    g = golden("wind_thermals")
+    p = O.thermal_hit_probability(g["t_aspect"].astype(np.float64))
+    assert p[:8].sum() == 0 and p[:, :10].sum() == 0 and (p[8:72, 10:90] > 0).all()
+    assert 1 / 2999 <= p[p > 0].min() and p.max() <= 1 / 999
+    # the Gaussian smoothing (zero padding) keeps almost all of the mass: E[mean(wt)] ~ mean(p) * E[lognormal]
+    expect = p.mean() * LOGN_MEAN
+    means = g["t_reference_means"]
+    sem = means.std(ddof=1) / np.sqrt(len(means))
+    assert abs(means.mean() - expect) < 4 * sem + 0.02 * expect
+    sm = O.smooth_thermals(g["t_seeds"].astype(np.float64))
+    assert np.allclose(sm, g["t_smoothed"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_gpu_wind_interpolation(golden, case):
+    from ssrs_b200 import layers
+    g = golden("wind_thermals")
+    rows, cols, res, xg, yg = _grid(g)
+    ws, wd = layers.interpolate_wind_to_grid(g[f"{case}_x"], g[f"{case}_y"], g[f"{case}_speed"], g[f"{case}_dirn"],
+                                             0.0, 0.0, res, (rows, cols))
+    ws, wd = ws.cpu().numpy().astype(np.float64), wd.cpu().numpy().astype(np.float64)
+    ref_s, ref_d = g[f"{case}_ws"], g[f"{case}_wd"]
+    nan_ref = np.isnan(ref_s)
+    # hull membership may differ only for cells within rounding of a hull edge
+    assert (np.isnan(ws) != nan_ref).sum() <= 2
+    ok = ~nan_ref & ~np.isnan(ws)
+    assert np.abs(ws[ok] - ref_s[ok]).max() <= 1e-5 * np.abs(ref_s[ok]).max()          # float32 output vs float64
+    dd = np.abs(wd[ok] - ref_d[ok])
+    dd = np.minimum(dd, 360.0 - dd)                                                      # directions wrap at north
+    assert dd.max() <= 1e-5 * 360.0
+
+
+@pytest.mark.gpu
+def test_gpu_wind_interpolation_feeds_stage1(golden):
+    """The interpolated rasters drive the per-cell-wind stencil exactly like the reference's
+    compute_orographic_updrafts_using_wtk (simulator.py:200-215)."""
+    from ssrs_b200 import layers
+    from ssrs_b200.synth import synthetic_dem
+    g = golden("wind_thermals")
+    rows, cols, res, xg, yg = _grid(g)
+    z = synthetic_dem(rows, cols, res, seed=5, rough_rms=10.0)
+    ws, wd = layers.interpolate_wind_to_grid(g["a_x"], g["a_y"], g["a_speed"], g["a_dirn"], 0.0, 0.0, res, (rows, cols))
+    oro = layers.updraft_fields(z, res, ws, wd, 0.75, want=("orograph",))["orograph"]
+    oro = oro if isinstance(oro, np.ndarray) else oro.cpu().numpy()
+    _, _, ref_oro, _ = O.updraft_pipeline(z, res, g["a_ws"], g["a_wd"], 0.75)
+    assert np.abs(oro - ref_oro).max() <= 1e-5 * max(1.0, np.abs(ref_oro).max())
+
+
+@pytest.mark.gpu
+def test_gpu_gaussian_blur_matches_scipy(golden):
+    from ssrs_b200 import layers
+    g = golden("wind_thermals")
+    out = layers.gaussian_filter_constant(g["t_seeds"], 4.0, 4.0)
+    assert np.abs(out - g["t_smoothed"]).max() <= 1e-5 * np.abs(g["t_smoothed"]).max()
+    rng = np.random.RandomState(0)
+    x = rng.rand(37, 53).astype(np.float32)                      # ragged size, kernel wider than the borders
+    from scipy import ndimage
+    ref = ndimage.gaussian_filter(x.astype(np.float64), sigma=2.5, mode='constant', truncate=3.0)
+    assert np.abs(layers.gaussian_filter_constant(x, 2.5, 3.0) - ref).max() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_gpu_thermals_distribution(golden):
+    """Distributional parity (the reference draws from numpy's global stream cell by cell)."""
+    from ssrs_b200 import layers
+    g = golden("wind_thermals")
+    asp = np.tile(g["t_aspect"], (10, 10))                      # 800 x 1000 cells: ~400 seeds per realisation
+    p = O.thermal_hit_probability(asp.astype(np.float64))
+    seeds = layers.thermal_seeds(asp, 2.0, seed=123)
+    assert (seeds[p == 0] == 0).all()                           # 10 % border stays empty
+    hits = seeds > 0
+    n_exp, n_sd = p.sum(), np.sqrt((p * (1 - p)).sum())
+    assert abs(hits.sum() - n_exp) <= 4 * n_sd
+    logs = np.log(seeds[hits].astype(np.float64))
+    assert abs(logs.mean() - 5.0) <= 4 * 0.5 / np.sqrt(hits.sum()) and abs(logs.std() - 0.5) <= 0.06
+    assert not np.array_equal(layers.thermal_seeds(asp, 2.0, seed=124), seeds)
+    assert np.array_equal(layers.thermal_seeds(asp, 2.0, seed=123), seeds)       # counter-based: reproducible
+    # full compute_thermals on the fixture's grid: mean over realisations against the reference's realisations
+    means = np.array([layers.compute_thermals(g["t_aspect"], 2.0, seed=s).mean() for s in range(40)])
+    ref = g["t_reference_means"]
+    sem = np.sqrt(means.var(ddof=1) / len(means) + ref.var(ddof=1) / len(ref))
+    assert abs(means.mean() - ref.mean()) <= 4 * sem
