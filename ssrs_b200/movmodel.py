@@ -159,6 +159,27 @@ class TrackBatchResult:
         return [tr[i, :lens[i]].copy() for i in range(self.n_tracks)]
 
 
+    def packed(self):
+        """(offsets int64 [n + 1], points int16 [total, 2]) on the host — the packed on-disk form (trackio.py),
+        gathered on the device from the step-major trajectory buffer."""
+        torch = N.require_cuda()
+        if self.traj is None:
+            raise ValueError("trajectories were not recorded (record=False)")
+        lens = self.traj_len.to(torch.int64)
+        if bool((lens > self.traj_cap).any()):
+            raise ValueError("traj_cap was smaller than the longest track")
+        offsets = torch.zeros(self.n_tracks + 1, dtype=torch.int64, device=lens.device)
+        torch.cumsum(lens, 0, out=offsets[1:])
+        points_parts = []
+        chunk = max(1, (1 << 28) // max(1, self.traj_cap))           # bound the boolean mask to ~256 MB
+        for lo in range(0, self.n_tracks, chunk):
+            hi = min(self.n_tracks, lo + chunk)
+            mask = torch.arange(self.traj_cap, device=lens.device)[None, :] < lens[lo:hi, None]
+            points_parts.append(self.traj[:, lo:hi].permute(1, 0, 2)[mask].cpu())
+        points = torch.cat(points_parts) if points_parts else torch.zeros((0, 2), dtype=torch.int16)
+        return offsets.cpu().numpy(), points.numpy()
+
+
 def interleave_fields(updraft, potential):
     """{updraft, potential} -> float32 [rows, cols, 2] on the device (one 8-byte gather per cell)."""
     torch = N.require_cuda()

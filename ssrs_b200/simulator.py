@@ -38,6 +38,7 @@ import numpy as np
 
 from . import _native as N
 from . import dist as _dist
+from . import trackio
 from .config import Config
 from .layers import get_above_threshold_speed, updraft_fields
 from .movmodel import MovModel, get_starting_indices, interleave_fields, simulate_tracks_batch
@@ -306,14 +307,24 @@ class Simulator(Config):
                 print(f'took {_elapsed(t0)}', flush=True)
                 self._presence[id_str] = presence
                 fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
-                if record:
+                if record and n <= TRACKS_PKL_LIMIT:
                     tracks = res.tracks()
                     tracks = _dist.gather_tracks(tracks)
                     if _dist.rank() == 0:
-                        with open(f'{fname}.pkl', 'wb') as fobj:
-                            pickle.dump(tracks, fobj)
-                elif _dist.rank() == 0:
+                        trackio.save_tracks_pickle(fname, tracks)        # the reference's file (:383-386)
+                elif record:
+                    # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
+                    off, pts = res.packed()
+                    suffix = '' if _dist.world_size() == 1 else f'_part{_dist.rank()}of{_dist.world_size()}'
+                    trackio.save_tracks_packed(f'{fname}{suffix}', off, pts)
+                if not record and _dist.rank() == 0:
                     np.savez_compressed(f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
+
+    def load_tracks(self, case_id: Optional[str] = None, real_id: int = 0):
+        """The stored tracks of (case, realisation) as the reference's list of int16 [L, 2] arrays, from either
+        on-disk format (single-rank runs)."""
+        case_id = self.case_ids[0] if case_id is None else case_id
+        return trackio.load_tracks(self._get_tracks_fname(case_id, real_id, self.mode_data_dir))
 
     def presence_counts(self, case_id: Optional[str] = None, real_id: int = 0) -> np.ndarray:
         """int32 visit counts of the last simulate_tracks() (reference compute_presence_counts, movmodel.py:410-419)."""
