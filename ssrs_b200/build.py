@@ -52,7 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), "-c", s, "-o", o])
+            jobs.append([nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), *os.environ.get("SSRS_NVCC_FLAGS", "").split(),
+                         "-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -162,9 +162,12 @@ inline int pfor_range(int64_t i0, int64_t i1, stream_t s, F f) {
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+#ifndef SSRS_PFOR2D_MIN_BLOCKS
+#define SSRS_PFOR2D_MIN_BLOCKS 8
+#endif
 // raster kernels: one thread per cell, 32 x 8 cells per CTA; f(row, col)
 template <class F>
-__global__ void __launch_bounds__(256) pfor2d_kernel(int r0, int r1, int cols, F f) {
+__global__ void __launch_bounds__(256, SSRS_PFOR2D_MIN_BLOCKS) pfor2d_kernel(int r0, int r1, int cols, F f) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int r = r0 + blockIdx.y * 8 + threadIdx.y;
     if (r < r1 && c < cols) f(r, c);
@@ -229,7 +232,7 @@ inline int preduce_sum2_range(int64_t i0, int64_t i1, stream_t s, double* out0, 
 }
 // the same over a raster: CTAs stride over 32 x 8 tiles in a fixed order
 template <class F>
-__global__ void __launch_bounds__(256) reduce2d_kernel(int r0, int rows, int cols, int tiles_x, int64_t tiles, double* partial, F f) {
+__global__ void __launch_bounds__(256, SSRS_PFOR2D_MIN_BLOCKS) reduce2d_kernel(int r0, int rows, int cols, int tiles_x, int64_t tiles, double* partial, F f) {
     double s0 = 0.0, s1 = 0.0;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {

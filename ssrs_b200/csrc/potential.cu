@@ -241,7 +241,7 @@ struct Level {
     i64* rowptr = nullptr; int* col = nullptr; double* val = nullptr;       // CSR (levels >= 1)
     int* agg = nullptr; i64 nc = 0; i64* memptr = nullptr; int* mem = nullptr;  // map to the next level
     i64* sptr = nullptr; int* ecol = nullptr; float* eval = nullptr; i64 ell_entries = 0;   // sliced ELL, float32 (levels >= 1)
-    real *excess = nullptr, *dinv = nullptr;
+    float *excess = nullptr, *dinv = nullptr;                                 // per-row operator data, float32 like the entries
     real *x32 = nullptr, *b32 = nullptr, *t32 = nullptr, *r32 = nullptr;      // cycle vectors (levels >= 1)
     // row-sharded solve: ownership of this level's nodes and, per part, the index range its rows reference
     Parts parts;
@@ -461,7 +461,7 @@ int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
 // rounding inside the cycle cannot change the solution it converges to.
 struct Fine32 {
     const float *wE, *wN, *wNE, *wNW;   // forward link weights, 0 where the neighbour is outside the grid
-    const real* dinv;                  // 1 / (sum of the eight link weights); 0 at Dirichlet nodes
+    const float* dinv;                 // 1 / (sum of the eight link weights); 0 at Dirichlet nodes
     const float* kd;                    // conductivity, sign bit = Dirichlet
     int rows, cols;
 };
@@ -491,8 +491,8 @@ SSRS_HD inline real fine_apply32(const Fine32& F, int r, int c, const X& x) {
 
 struct VecF { const real* p; SSRS_HD real operator()(i64 j) const { return p[j]; } };
 // x1 = omega D^-1 b, the first Jacobi sweep from a zero guess, evaluated on the fly
-struct FirstSweepFine { const double* b; const real* dinv; real omega; SSRS_HD real operator()(i64 j) const { return omega * dinv[j] * (real)b[j]; } };
-struct FirstSweepF { const real* b; const real* dinv; real omega; SSRS_HD real operator()(i64 j) const { return omega * dinv[j] * b[j]; } };
+struct FirstSweepFine { const double* b; const float* dinv; real omega; SSRS_HD real operator()(i64 j) const { return omega * dinv[j] * (real)b[j]; } };
+struct FirstSweepF { const real* b; const float* dinv; real omega; SSRS_HD real operator()(i64 j) const { return omega * dinv[j] * b[j]; } };
 
 // All cycle kernels take the range they compute ([r0, r1) rows of the fine grid, [i0, i1) nodes of a coarse
 // level): the whole level on one GPU, the owned slab in the row-sharded solve.
@@ -506,7 +506,7 @@ inline int fine_first32(const Fine32 F, int r0, int r1, const double* b, real* x
 inline int fine_first_residual32(const Fine32 F, int r0, int r1, const double* b, real* x, real* res, real omega, stream_t st) {
     return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
-        if (F.dinv[i] == (real)0.0) { x[i] = (real)0.0; res[i] = (real)0.0; return; }
+        if (F.dinv[i] == 0.0f) { x[i] = (real)0.0; res[i] = (real)0.0; return; }
         const FirstSweepFine x1 = {b, F.dinv, omega};
         x[i] = x1(i);
         res[i] = (real)b[i] - fine_apply32(F, r, c, x1);
@@ -515,7 +515,7 @@ inline int fine_first_residual32(const Fine32 F, int r0, int r1, const double* b
 inline int fine_residual32(const Fine32 F, int r0, int r1, const double* b, const real* x, real* res, stream_t st) {
     return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
-        if (F.dinv[i] == (real)0.0) { res[i] = (real)0.0; return; }
+        if (F.dinv[i] == 0.0f) { res[i] = (real)0.0; return; }
         res[i] = (real)b[i] - fine_apply32(F, r, c, VecF{x});
     });
 }
@@ -535,8 +535,8 @@ struct Ell {
     const i64* sptr;        // [slices + 1]
     const int* col;
     const float* val;
-    const real* excess;    // a_ii + sum_off a_ij
-    const real* dinv;      // 1 / a_ii
+    const float* excess;   // a_ii + sum_off a_ij (formed in float64, rounded once)
+    const float* dinv;     // 1 / a_ii
     i64 n;
 };
 template <class X>
@@ -545,7 +545,16 @@ SSRS_HD inline real ell_apply(const Ell& e, i64 i, const X& x) {
     const i64 p1 = e.sptr[s + 1];
     const real xi = x(i);
     real acc = (real)0.0;
-    for (i64 p = e.sptr[s] + (i & 31); p < p1; p += 32) acc += e.val[p] * (x(e.col[p]) - xi);
+    i64 p = e.sptr[s] + (i & 31);
+    // four entries per trip: the column indices, then the gathers they address, are independent loads — a row's
+    // entries are otherwise a chain of dependent L2 round trips (the small levels are pure latency)
+    for (; p + 96 < p1; p += 128) {
+        const int c0 = e.col[p], c1 = e.col[p + 32], c2 = e.col[p + 64], c3 = e.col[p + 96];
+        const float v0 = e.val[p], v1 = e.val[p + 32], v2 = e.val[p + 64], v3 = e.val[p + 96];
+        const real x0 = x(c0), x1 = x(c1), x2 = x(c2), x3 = x(c3);
+        acc += (v0 * (x0 - xi) + v1 * (x1 - xi)) + (v2 * (x2 - xi) + v3 * (x3 - xi));
+    }
+    for (; p < p1; p += 32) acc += e.val[p] * (x(e.col[p]) - xi);
     return e.excess[i] * xi + acc;
 }
 inline int ell_first32(const Ell e, i64 i0, i64 i1, const real* b, real* x, real omega, stream_t st) {
@@ -594,6 +603,7 @@ struct Hierarchy {
     const ssrs_comm* comm = nullptr;
     int rank = 0, nparts = 1;
     int lrep = 1 << 30;        // levels >= lrep are computed redundantly by every rank
+    bool fuse_coarse_first = false;   // coarse levels: first sweep fused into the residual pass (two gathers per entry) or separate (one)
     stream_t st = nullptr;
 };
 
@@ -635,13 +645,13 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
     const CsrGraph g = csr_of(L);
     const i64 n = L.n, slices = (n + 31) / 32;
     AMG_ALLOC(L.sptr, i64, slices + 1);
-    AMG_ALLOC(L.excess, real, n);
-    AMG_ALLOC(L.dinv, real, n);
+    AMG_ALLOC(L.excess, float, n);
+    AMG_ALLOC(L.dinv, float, n);
     AMG_ALLOC(L.x32, real, n);
     AMG_ALLOC(L.b32, real, n);
     AMG_ALLOC(L.t32, real, n);
     AMG_ALLOC(L.r32, real, n);
-    i64* sptr = L.sptr; real* excess = L.excess; real* dinv = L.dinv;
+    i64* sptr = L.sptr; float* excess = L.excess; float* dinv = L.dinv;
     AMG_TRY(pfor(slices + 1, st, [=] SSRS_HD(i64 s) {
         i64 width = 0;
         if (s < slices)
@@ -670,8 +680,8 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
             p += 32;
         }
         for (; p < p1; p += 32) { ecol[p] = (int)i; eval[p] = 0.0f; }
-        excess[i] = (real)(d + off);
-        dinv[i] = (real)(1.0 / d);
+        excess[i] = (float)(d + off);
+        dinv[i] = (float)(1.0 / d);
     }));
     // row-sharded solve: the index range each part's rows reference (its own range plus the ghost zones)
     const Parts P = L.parts;
@@ -772,7 +782,7 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
         i64 i0, i1;
         own_range(H, l, i0, i1);
         AMG_RC(exchange_ghosts(H, l, L.b32, sizeof(real)));
-        if (nu == 1) { AMG_TRY(ell_first_residual32(e, i0, i1, L.b32, L.x32, L.r32, om, st)); }
+        if (nu == 1 && H.fuse_coarse_first) { AMG_TRY(ell_first_residual32(e, i0, i1, L.b32, L.x32, L.r32, om, st)); }
         else {
             AMG_TRY(ell_first32(e, i0, i1, L.b32, L.x32, om, st));
             for (int s = 1; s < nu; ++s) {
@@ -780,7 +790,12 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
                 AMG_TRY(ell_jacobi32(e, i0, i1, L.b32, L.x32, L.t32, om, st));
                 real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
             }
-            AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
+            // (the first sweep is elementwise, so the ghosts of x can be formed locally from the exchanged b)
+            if (nu == 1 && H.comm != nullptr && l < H.lrep) {
+                const i64 g0 = L.ref_lo[H.rank], g1 = L.ref_hi[H.rank];
+                AMG_TRY(ell_first32(e, g0, i0, L.b32, L.x32, om, st));
+                AMG_TRY(ell_first32(e, i1, g1, L.b32, L.x32, om, st));
+            } else AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
             AMG_TRY(ell_residual32(e, i0, i1, L.b32, L.x32, L.r32, st));
         }
         AMG_RC(restrict_to(l, L.r32));
@@ -914,6 +929,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     if (getenv("SSRS_X_OC")) H.overcorrect = (float)atof(getenv("SSRS_X_OC"));
     if (getenv("SSRS_X_OMEGA")) H.omega = (float)atof(getenv("SSRS_X_OMEGA"));
     if (getenv("SSRS_X_NU")) H.nu = atoi(getenv("SSRS_X_NU"));
+    if (getenv("SSRS_X_FUSEC")) H.fuse_coarse_first = atoi(getenv("SSRS_X_FUSEC")) != 0;
 
     // Dirichlet nodes arrive as the reference's column-major ids (movmodel.py:25-29): i = col*nrow + row
     std::vector<int> bidx((size_t)n_bnodes);
@@ -969,10 +985,10 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         }
     }
     {
-        float* wf; real* dinv; double* wd;
+        float *wf, *dinv; double* wd;
         AMG_ALLOC(wf, float, 4 * n);
         AMG_ALLOC(wd, double, 4 * n);
-        AMG_ALLOC(dinv, real, n);
+        AMG_ALLOC(dinv, float, n);
         const FineGraph fgw = H.fine;
         AMG_TRY(pfor2d(rows, cols, st, [=] SSRS_HD(int r, int c) {
             const i64 i = (i64)r * cols + c;
@@ -990,7 +1006,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         F.wE = wf; F.wN = wf + n; F.wNE = wf + 2 * n; F.wNW = wf + 3 * n; F.dinv = dinv; F.kd = kd; F.rows = rows; F.cols = cols;
         AMG_TRY(pfor2d(rows, cols, st, [=] SSRS_HD(int r, int c) {       // Jacobi diagonal of the float32 operator
             const i64 i = (i64)r * cols + c;
-            if (fgw.excluded(i)) { dinv[i] = (real)0.0; return; }
+            if (fgw.excluded(i)) { dinv[i] = 0.0f; return; }
             const bool hW = c > 0, hE = c < cols - 1, hS = r > 0, hN = r < rows - 1;
             real wS = hS ? F.wN[i - cols] : (real)0.0, wSW = (hS && hW) ? F.wNE[i - cols - 1] : (real)0.0;
             if (c == cols - 1 && hS && hN) {
@@ -999,7 +1015,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             }
             const real d = ((F.wE[i] + (hW ? F.wE[i - 1] : (real)0.0)) + (F.wN[i] + wS)) +
                             ((F.wNE[i] + wSW) + (F.wNW[i] + ((hS && hE) ? F.wNW[i - cols + 1] : (real)0.0)));
-            dinv[i] = (real)1.0 / d;
+            dinv[i] = (float)((real)1.0 / d);
         }));
         H.f32 = F;
         AMG_ALLOC(H.xf, real, n);
@@ -1093,7 +1109,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     // the true residual has flattened — and the result is accepted when the true residual is below floor/2.
     double floor2 = 0.0, bmax = 0.0;
     for (int64_t q = 0; q < n_bnodes; ++q) bmax = fabs(bvalues_host[q]) > bmax ? fabs(bvalues_host[q]) : bmax;
-    { const real* dinv = H.f32.dinv; const double scale = 0.5 * 2.220446049250313e-16 * bmax;
+    { const float* dinv = H.f32.dinv; const double scale = 0.5 * 2.220446049250313e-16 * bmax;
       AMG_TRY(preduce_sum(n, st, &floor2, [=] SSRS_HD(i64 i) { const double di = (double)dinv[i]; const double e = di > 0.0 ? scale / di : 0.0; return e * e; })); }
     const double floor_rel = (r0 > 0.0) ? sqrt(floor2) / r0 : 0.0;
     if (trace) fprintf(stderr, "ssrs_potential_solve: r0 %.3e attainable relative residual ~ %.3e\n", r0, floor_rel);

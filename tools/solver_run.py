@@ -7,7 +7,8 @@ from ssrs_b200.synth import synthetic_dem
 rows, cols, res = (int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])) if len(sys.argv) > 3 else (5000, 6000, 10.0)
 zs = torch.from_numpy(synthetic_dem(256, 320, res, seed=1)).cuda()
 ks = layers.updraft_fields(zs, res, 10.0, 270.0, 0.75, want=("updraft",))["updraft"]
-solve_potential_device(ks, 0.0, strict=False)
+if not os.environ.get('SSRS_NO_WARMUP'):
+    solve_potential_device(ks, 0.0, strict=False)
 z = torch.from_numpy(synthetic_dem(rows, cols, res)).cuda()
 K = layers.updraft_fields(z, res, 10.0, 270.0, 0.75, want=("updraft",))["updraft"]
 torch.cuda.synchronize(); t0 = time.time()
