@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
     int hcount = 1;
     unsigned run_mask = 0x1EF;            // AND over the whole history (memory == 0)
     unsigned rng_c = 0, rng_d = 0;        // second half of the last Philox block
+    const bool fast_lane = P.nu_is_one && P.uniforms == nullptr && P.traj == nullptr && P.presence != nullptr;
 
     while (true) {
         if (!alive) {
@@ -280,6 +281,37 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
             if (P.traj != nullptr && P.traj_cap > 0) P.traj[t] = make_short2((short)row, (short)col);
             if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
             alive = true;
+        }
+        // Fast lane: pairs of ordinary steps (interior cell, previous move known, nu == 1, Philox stream, counts only,
+        // no trajectory store) run in a tight loop without the bookkeeping below; one Philox block feeds both steps
+        // of a pair, so there is no parity branch.  Anything else — first step, burn-in relocation or exit near the
+        // border, the move limit — leaves the loop and takes the general step.  Same arithmetic, same draws.
+        if (HAS_FIELDS && !EXACT && MEM1 && fast_lane && last != 4u && (k & 1) == 0) {
+            const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
+            while (row > 1 && row < nr - 2 && col > 0 && col < nc - 2 && k + 1 < kmax) {
+                unsigned a, b, cc, dd;
+                int lin = row * nc + col;
+                const float2* base = P.fields + lin;
+                int4 cand = s_cand[last];
+                float2 fc = __ldg(base), f0 = __ldg(base + cand.x), f1 = __ldg(base + cand.y), f2 = __ldg(base + cand.z);
+                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, (unsigned)P.seed,
+                              (unsigned)(P.seed >> 32), a, b, cc, dd);
+                int idx = choose_fast3<true, true>(P, base, nc, 0u, cand.w & 15, (cand.w >> 4) & 15, (cand.w >> 8) & 15,
+                                                   fc, f0, f1, f2, uniform52(a, b));
+                int dr = ((idx * 11) >> 5) - 1, dc = idx - 3 * (dr + 1) - 1;
+                row += dr; col += dc; ++k; last = (unsigned)idx;
+                atomicAdd(P.presence + (lin + dr * nc + dc), 1u);
+                if (!(row > 1 && row < nr - 2 && col > 0 && col < nc - 2)) { rng_c = cc; rng_d = dd; break; }
+                lin = row * nc + col;
+                base = P.fields + lin;
+                cand = s_cand[last];
+                fc = __ldg(base); f0 = __ldg(base + cand.x); f1 = __ldg(base + cand.y); f2 = __ldg(base + cand.z);
+                idx = choose_fast3<true, true>(P, base, nc, 0u, cand.w & 15, (cand.w >> 4) & 15, (cand.w >> 8) & 15,
+                                               fc, f0, f1, f2, uniform52(cc, dd));
+                dr = ((idx * 11) >> 5) - 1; dc = idx - 3 * (dr + 1) - 1;
+                row += dr; col += dc; ++k; last = (unsigned)idx;
+                atomicAdd(P.presence + (lin + dr * nc + dc), 1u);
+            }
         }
         int r = row, c = col;
         bool finish = k >= kmax;                                            // movmodel.py:285

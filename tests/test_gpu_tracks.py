@@ -106,6 +106,13 @@ def test_philox_matches_c_oracle(mem, nu, dirn):
     for t in range(0, n, 37):
         L = min(ref["traj_len"][t], cap)
         assert np.array_equal(traj[t, :L], ref["traj"][t, :L])
+    # counts-only launch (no trajectory store): with memory 1 and nu 1 this takes the kernel's fast lane
+    # (pairs of steps per Philox block); it must reproduce the same tracks
+    res2 = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, updraft_field=U,
+                                    potential_field=P, seed=1234, track_id0=17)
+    assert res2.total_steps == ref["total_steps"]
+    assert np.array_equal(res2.traj_len.cpu().numpy(), ref["traj_len"])
+    assert np.array_equal(res2.presence.cpu().numpy(), ref["presence"])
 
 
 def test_sharding_invariance():
