@@ -147,3 +147,33 @@ def test_snapshot_mode_wind_sites_and_thermals(tmp_path):
     sim2 = Simulator(cfg.__class__(**{**cfg.__dict__, "run_name": "snap3"}), elevation=z, wind_points=(xl, yl),
                      wind_cases={"y2014m12d01h15": (spd, drn)})
     assert np.array_equal(np.load(os.path.join(sim2.mode_data_dir, "y2014m12d01h15_r0_thermals.npy")), th)
+
+
+def test_seasonal_mode_three_cases(tmp_path):
+    """BASELINE config 5 in miniature: several wind cases (the reference's seasonal loop over case_ids,
+    simulator.py:200-215, 348-386, 520-546): one orograph, potential, track set and presence map per case; the
+    summary map is the normalised sum of the per-case maps."""
+    from ssrs_b200 import Config, Simulator
+    from ssrs_b200.synth import seasonal_wind_conditions, synthetic_dem
+    rows, cols, res = 120, 160, 100.0
+    z = synthetic_dem(rows, cols, res, seed=4)
+    spd, drn = seasonal_wind_conditions(3, seed=11)
+    cases = {f"y2015m0{i + 3}d10h12": (float(spd[i]), float(drn[i])) for i in range(3)}
+    cfg = Config(run_name="seas", out_dir=str(tmp_path), sim_seed=5, sim_mode="seasonal", region_width_km=(16., 12.),
+                 resolution=res, track_count=200, track_start_region=(2, 14, 0.5, 1), track_direction=0.)
+    sim = Simulator(cfg, elevation=z, wind_cases=cases)
+    assert sim.case_ids == list(cases)
+    sim.simulate_tracks()
+    maps = []
+    for i, cid in enumerate(cases):
+        oro = np.load(os.path.join(sim.mode_data_dir, f"{cid}_orograph.npy"))
+        _, _, oro_ref, _ = O.updraft_pipeline(z, res, float(spd[i]), float(drn[i]), 0.75)
+        assert np.abs(oro - oro_ref).max() <= 1e-5 * max(oro_ref.max(), 1e-30)
+        assert os.path.exists(os.path.join(sim.mode_data_dir, f"{cid}_d0_t75_fluidflow_r0_potential.npy"))
+        cnt = sim.presence_counts(cid)
+        assert cnt.sum() == sim._presence[sim._get_id_string(cid, 0)].sum().item() and cnt.sum() > 200
+        sm = O.smooth_presence(cnt, 5)
+        maps.append(sm / sm.max())
+    summ = sim.plot_presence_map(radius=500.)
+    ref = np.sum(maps, axis=0)
+    assert np.allclose(summ, ref / ref.max(), rtol=1e-5, atol=1e-6)

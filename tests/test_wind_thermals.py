@@ -111,3 +111,30 @@ def test_gpu_thermals_distribution(golden):
     ref = g["t_reference_means"]
     sem = np.sqrt(means.var(ddof=1) / len(means) + ref.var(ddof=1) / len(ref))
     assert abs(means.mean() - ref.mean()) <= 4 * sem
+
+
+@pytest.mark.gpu
+def test_gpu_wind_interpolation_full_size():
+    """BASELINE config 4 shape: ~800 sites on a jittered 2 km lattice -> (5000, 6000) rasters; compared with
+    griddata on every 40th grid line (griddata over all 3e7 cells takes minutes on the host)."""
+    import time
+    import torch
+    from ssrs_b200 import layers
+    from ssrs_b200.synth import synthetic_wind_lattice
+    rows, cols, res = 5000, 6000, 10.0
+    xl, yl, spd, drn = synthetic_wind_lattice(rows, cols, res, spacing_m=2000.0, seed=7)
+    tri = layers.delaunay_triangles(xl, yl)
+    layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), triangles=tri)       # warm-up
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ws, wd = layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), triangles=tri)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"interpolate_wind_to_grid {len(xl)} sites -> {rows}x{cols}: {dt * 1e3:.2f} ms")
+    assert not torch.isnan(ws).any() and not torch.isnan(wd).any()          # the lattice is padded beyond the region
+    xg = np.linspace(0.0, (cols - 1) * res, cols)[::40]
+    yg = np.linspace(0.0, (rows - 1) * res, rows)[::40]
+    ref_s, ref_d = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg)
+    got_s = ws[::40, ::40].cpu().numpy().astype(np.float64)
+    got_d = wd[::40, ::40].cpu().numpy().astype(np.float64)
+    assert np.abs(got_s - ref_s).max() <= 1e-5 * ref_s.max()
+    dd = np.abs(got_d - ref_d); dd = np.minimum(dd, 360.0 - dd)
+    assert dd.max() <= 1e-5 * 360.0
