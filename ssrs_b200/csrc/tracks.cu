@@ -197,6 +197,12 @@ __device__ __noinline__ int choose_fast_general(const TrackParams& P, const floa
     return idx >= 0 ? idx : last_pos;
 }
 
+// fmax((double)x, 1e-6) (movmodel.py:294-295) for a float32 x, decided in float32: (double)x < 1e-6 exactly when
+// x <= float32(1e-6) = 9.99999997e-07, the largest float32 below 1e-6; NaN -> 1e-6 like fmax.
+__device__ __forceinline__ double clip_updraft(float x) {
+    return (x > 9.99999997475242707e-07f) ? (double)x : 1e-06;
+}
+
 // the three neighbours within 45 degrees of the previous move, ascending flat index, 4 bits each
 constexpr unsigned long long C3_A = (0x310ULL) | (0x210ULL << 12) | (0x521ULL << 24) | (0x630ULL << 36) | (0x000ULL << 48);
 constexpr unsigned long long C3_B = (0x852ULL) | (0x763ULL << 12) | (0x876ULL << 24) | (0x875ULL << 36);
@@ -220,8 +226,8 @@ __device__ __forceinline__ int choose_fast3(const TrackParams& P, const float2* 
         const float d1 = __fmul_rn(__fsub_rn(fc.y, f1.y), n1);
         const float d2 = __fmul_rn(__fsub_rn(fc.y, f2.y), n2);
         any_nan = (e0 && d0 != d0) || (e1 && d1 != d1) || (e2 && d2 != d2);
-        const double uc = fmax((double)fc.x, 1e-06);
-        const double u0 = fmax((double)f0.x, 1e-06), u1 = fmax((double)f1.x, 1e-06), u2 = fmax((double)f2.x, 1e-06);
+        const double uc = clip_updraft(fc.x);
+        const double u0 = clip_updraft(f0.x), u1 = clip_updraft(f1.x), u2 = clip_updraft(f2.x);
         const double s0 = uc + u0, s1 = uc + u1, s2 = uc + u2;
         if (e0 && d0 > 0.0f) q0 = ((double)d0 * u0) * (s1 * s2);
         if (e1 && d1 > 0.0f) q1 = ((double)d1 * u1) * (s0 * s2);
