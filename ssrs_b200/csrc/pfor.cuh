@@ -54,6 +54,18 @@ inline int preduce_sum2_range(int64_t i0, int64_t i1, stream_t, double* out0, do
     *out0 = s0; *out1 = s1;
     return 0;
 }
+// one "warp" per row: partial(i, lane) for lane = 0..31 is summed and handed to finish(i, total)
+template <class P, class Fin>
+inline int pfor_warp_rows(int64_t i0, int64_t i1, stream_t, P partial, Fin finish) {
+    for (int64_t i = i0; i < i1; ++i) {
+        double part[32];
+        for (int lane = 0; lane < 32; ++lane) part[lane] = partial(i, lane);
+        for (int o = 16; o > 0; o >>= 1)
+            for (int lane = 0; lane < o; ++lane) part[lane] += part[lane + o];      // the shuffle tree's order
+        finish(i, part[0]);
+    }
+    return 0;
+}
 template <class F>
 inline int pfor2d_rows(int r0, int r1, int cols, stream_t, F f) {
     for (int r = r0; r < r1; ++r)
@@ -177,6 +189,28 @@ inline int pfor2d_rows(int r0, int r1, int cols, stream_t s, F f) {
     if (r1 <= r0 || cols <= 0) return 0;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((r1 - r0 + 7) / 8));
     pfor2d_kernel<<<grid, dim3(32, 8), 0, s>>>(r0, r1, cols, f);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// one warp per row (rows of the small coarse levels are long and few: a thread per row would walk its entries as a
+// chain of dependent loads): partial(i, lane) is summed over the warp by a shuffle tree, lane 0 calls finish(i, total)
+template <class P, class Fin>
+__global__ void __launch_bounds__(256) pfor_warp_rows_kernel(int64_t i0, int64_t i1, P partial, Fin finish) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = i0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < i1; i += warps) {
+        double v = partial(i, lane);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) finish(i, v);
+    }
+}
+template <class P, class Fin>
+inline int pfor_warp_rows(int64_t i0, int64_t i1, stream_t s, P partial, Fin finish) {
+    const int64_t n = i1 - i0;
+    if (n <= 0) return 0;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > grid_cap()) blocks = grid_cap();
+    pfor_warp_rows_kernel<<<(int)blocks, 256, 0, s>>>(i0, i1, partial, finish);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -573,13 +573,38 @@ inline int ell_residual32(const Ell e, i64 i0, i64 i1, const real* b, const real
 inline int ell_jacobi32(const Ell e, i64 i0, i64 i1, const real* b, const real* x, real* xn, real omega, stream_t st) {
     return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { xn[i] = x[i] + omega * e.dinv[i] * (b[i] - ell_apply(e, i, VecF{x})); });
 }
-// bc_I = sum of the residual over the members of aggregate I (members ascending: deterministic), I in [I0, I1)
-inline int restrict32(const Level& L, i64 I0, i64 I1, const real* res, real* bc, stream_t st) {
+// Small levels (<= SMALL_ROWS rows): rows are long (tens to hundreds of entries) and few, so a warp walks each row
+// of the CSR arrays instead of a thread walking an ELL row: same operator (float32-rounded entries, difference form),
+// a handful of coalesced trips instead of a chain of dependent gathers.
+constexpr i64 SMALL_ROWS = 32768;
+SSRS_HD inline real csr_row_partial(const CsrGraph& g, i64 i, int lane, const real* x) {
+    const real xi = x[i];
+    real acc = (real)0.0;
+    for (i64 k = g.rowptr[i] + lane; k < g.rowptr[i + 1]; k += 32) {
+        const i64 j = g.col[k];
+        if (j != i) acc += (real)(float)g.val[k] * (x[j] - xi);
+    }
+    return acc;
+}
+inline int csr_residual32(const CsrGraph g, const float* excess, i64 i0, i64 i1, const real* b, const real* x, real* res, stream_t st) {
+    return pfor_warp_rows(i0, i1, st, [=] SSRS_HD(i64 i, int lane) { return (double)csr_row_partial(g, i, lane, x); },
+                          [=] SSRS_HD(i64 i, double total) { res[i] = b[i] - (excess[i] * x[i] + (real)total); });
+}
+inline int csr_jacobi32(const CsrGraph g, const float* excess, const float* dinv, i64 i0, i64 i1, const real* b, const real* x,
+                        real* xn, real omega, stream_t st) {
+    return pfor_warp_rows(i0, i1, st, [=] SSRS_HD(i64 i, int lane) { return (double)csr_row_partial(g, i, lane, x); },
+                          [=] SSRS_HD(i64 i, double total) { xn[i] = x[i] + omega * dinv[i] * (b[i] - (excess[i] * x[i] + (real)total)); });
+}
+
+// bc_I = sum of the residual over the members of aggregate I (members ascending: deterministic), I in [I0, I1);
+// with x1 != nullptr also the next level's first sweep from a zero guess, x1_I = omega dinv_I bc_I
+inline int restrict32(const Level& L, i64 I0, i64 I1, const real* res, real* bc, real* x1, const float* dinv, real omega, stream_t st) {
     const i64* memptr = L.memptr; const int* mem = L.mem;
     return pfor_range(I0, I1, st, [=] SSRS_HD(i64 I) {
         real s = (real)0.0;
         for (i64 p = memptr[I]; p < memptr[I + 1]; ++p) s += res[mem[p]];
         bc[I] = s;
+        if (x1 != nullptr) x1[I] = omega * dinv[I] * s;
     });
 }
 inline int prolong_add32(const Level& L, i64 i0, i64 i1, real* x, const real* xc, real scale, stream_t st) {
@@ -590,7 +615,7 @@ inline int prolong_add32(const Level& L, i64 i0, i64 i1, real* x, const real* xc
 struct Hierarchy {
     FineGraph fine;
     std::vector<Level> lv;     // lv[0] = fine level (agg/mem only), lv[l>=1] CSR + ELL
-    double* cinv = nullptr;    // dense inverse of the coarsest operator, transposed (float64)
+    double* cinv = nullptr;    // dense inverse of the coarsest operator (float64, row-major)
     i64 cn = 0;
     int coarse_sweeps = 0;     // > 0: coarsest level too large for a dense inverse, Jacobi sweeps instead
     real omega = (real)0.8;        // Jacobi weight
@@ -609,6 +634,15 @@ struct Hierarchy {
 
 inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; g.parts = L.parts; return g; }
 inline Ell ell_of(const Level& L) { Ell e; e.sptr = L.sptr; e.col = L.ecol; e.val = L.eval; e.excess = L.excess; e.dinv = L.dinv; e.n = L.n; return e; }
+
+inline int level_residual(const Level& L, i64 i0, i64 i1, const real* b, const real* x, real* res, stream_t st) {
+    if (L.n <= SMALL_ROWS) return csr_residual32(csr_of(L), L.excess, i0, i1, b, x, res, st);
+    return ell_residual32(ell_of(L), i0, i1, b, x, res, st);
+}
+inline int level_jacobi(const Level& L, i64 i0, i64 i1, const real* b, const real* x, real* xn, real omega, stream_t st) {
+    if (L.n <= SMALL_ROWS) return csr_jacobi32(csr_of(L), L.excess, L.dinv, i0, i1, b, x, xn, omega, st);
+    return ell_jacobi32(ell_of(L), i0, i1, b, x, xn, omega, st);
+}
 
 // range of level l this rank computes
 inline void own_range(const Hierarchy& H, int l, i64& i0, i64& i1) {
@@ -718,11 +752,9 @@ int coarse_solve(Hierarchy& H, Level& C, stream_t st) {
         return SSRS_OK;
     }
     const double* inv = H.cinv; const real* b = C.b32; real* x = C.x32; const i64 n = C.n;
-    return pfor(n, st, [=] SSRS_HD(i64 i) {
-        double s = 0.0;
-        for (i64 j = 0; j < n; ++j) s += inv[j * n + i] * (double)b[j];
-        x[i] = (real)s;
-    });
+    return pfor_warp_rows(0, n, st,
+                          [=] SSRS_HD(i64 i, int lane) { double s = 0.0; for (i64 j = lane; j < n; j += 32) s += inv[i * n + j] * (double)b[j]; return s; },
+                          [=] SSRS_HD(i64 i, double total) { x[i] = (real)total; });
 }
 
 #define AMG_RC(expr) do { const int rc_ = (expr); if (rc_) return rc_; } while (0)
@@ -762,12 +794,15 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
     }
     // restriction to level l+1 covers the aggregates this rank owns there (all of their members are local);
     // entering the redundantly computed levels the pieces are gathered on every rank
+    // also writes the next level's first sweep when that level goes on to smooth (not the coarsest, not gathered)
+    bool first_done = false;
     auto restrict_to = [&](int l, const real* res) -> int {
         Level& C = H.lv[(size_t)l + 1];
         i64 c0 = 0, c1 = C.n;
         const bool gather = H.comm != nullptr && l < H.lrep && l + 1 >= H.lrep;
         if (H.comm != nullptr && l < H.lrep) { c0 = C.parts.lo[H.rank]; c1 = C.parts.lo[H.rank + 1]; }
-        AMG_TRY(restrict32(H.lv[(size_t)l], c0, c1, res, C.b32, st));
+        first_done = !gather && l + 1 < nl - 1 && !(nu == 1 && H.fuse_coarse_first);
+        AMG_TRY(restrict32(H.lv[(size_t)l], c0, c1, res, C.b32, first_done ? C.x32 : nullptr, C.dinv, om, st));
         if (gather) {
             i64 offs[SSRS_MAX_RANKS + 1];
             for (int q = 0; q <= H.nparts; ++q) offs[q] = C.parts.lo[q] * (i64)sizeof(real);
@@ -784,10 +819,10 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
         AMG_RC(exchange_ghosts(H, l, L.b32, sizeof(real)));
         if (nu == 1 && H.fuse_coarse_first) { AMG_TRY(ell_first_residual32(e, i0, i1, L.b32, L.x32, L.r32, om, st)); }
         else {
-            AMG_TRY(ell_first32(e, i0, i1, L.b32, L.x32, om, st));
+            if (!first_done) AMG_TRY(ell_first32(e, i0, i1, L.b32, L.x32, om, st));
             for (int s = 1; s < nu; ++s) {
                 AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
-                AMG_TRY(ell_jacobi32(e, i0, i1, L.b32, L.x32, L.t32, om, st));
+                AMG_TRY(level_jacobi(L, i0, i1, L.b32, L.x32, L.t32, om, st));
                 real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
             }
             // (the first sweep is elementwise, so the ghosts of x can be formed locally from the exchanged b)
@@ -796,20 +831,19 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
                 AMG_TRY(ell_first32(e, g0, i0, L.b32, L.x32, om, st));
                 AMG_TRY(ell_first32(e, i1, g1, L.b32, L.x32, om, st));
             } else AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
-            AMG_TRY(ell_residual32(e, i0, i1, L.b32, L.x32, L.r32, st));
+            AMG_TRY(level_residual(L, i0, i1, L.b32, L.x32, L.r32, st));
         }
         AMG_RC(restrict_to(l, L.r32));
     }
     AMG_RC(coarse_solve(H, H.lv[(size_t)nl - 1], st));
     for (int l = nl - 2; l >= 1; --l) {
         Level& L = H.lv[(size_t)l];
-        const Ell e = ell_of(L);
         i64 i0, i1;
         own_range(H, l, i0, i1);
         AMG_TRY(prolong_add32(L, i0, i1, L.x32, H.lv[(size_t)l + 1].x32, H.overcorrect, st));
         for (int s = 0; s < nu; ++s) {
             AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
-            AMG_TRY(ell_jacobi32(e, i0, i1, L.b32, L.x32, L.t32, om, st));
+            AMG_TRY(level_jacobi(L, i0, i1, L.b32, L.x32, L.t32, om, st));
             real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
         }
     }
@@ -846,12 +880,8 @@ int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
             else { const double f = colk[i] / p; if (f != 0.0) { D[e] -= f * rowD[j]; I[e] -= f * rowI[j]; } }
         }));
     }
-    double* IT;
-    AMG_ALLOC(IT, double, n * n);
-    AMG_TRY(pfor(n * n, st, [=] SSRS_HD(i64 e) { const i64 i = e / n, j = e - i * n; IT[j * n + i] = I[e]; }));
     AMG_TRY(sync(st));
-    pool.release(I);
-    H.cinv = IT; H.cn = n;
+    H.cinv = I; H.cn = n;
     return SSRS_OK;
 }
 
