@@ -110,7 +110,7 @@ SSRS_API int ssrs_release_workspace(void);
  * (identical, no communication; aggregates never straddle a slab boundary); the solve phase — V-cycles, operator
  * applications, Krylov vectors — runs on the owned slab only and exchanges one-row halos (fine level) or the few
  * boundary-adjacent entries (coarse levels) with the two neighbouring ranks before each operator application,
- * plus one scalar all-reduce per inner product.  Levels below ~64 k rows are computed redundantly.
+ * plus one scalar all-reduce per inner product.  Levels below 1e6 rows are computed redundantly.
  *
  * ssrs_comm is the transport: plain function pointers, so the product uses NCCL over NVLink
  * (ssrs_comm_create_nccl) and the CPU test build drives the same solver code over gloo.

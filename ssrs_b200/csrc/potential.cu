@@ -1060,8 +1060,10 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     // Row-sharded solve: a level stays distributed while it is large and every part's rows reference the
     // adjacent parts only; its aggregates must then not straddle a slab boundary.  From the first level that is
     // not (H.lrep) all ranks compute redundantly and coarsening is unconstrained again — constraining every
-    // level leaves a seam that the coarse levels never close and costs ~40 % more iterations.
-    const i64 rep_rows = getenv("SSRS_X_REPROWS") ? atoll(getenv("SSRS_X_REPROWS")) : 65536;
+    // level leaves a seam that the coarse levels never close and costs ~40 % more iterations.  Measured on 4 GPUs
+    // (5000 x 6000 / 10000 x 12000): threshold 65 536 rows -> 56 / 47 iterations, 166 / 382 ms; 1.2e6 -> 43 / 44,
+    // 129 / 362 ms; 5e6 -> 42 / 44, 155 / 382 ms (single GPU: 41 / 43 iterations, 283 / 1128 ms).
+    const i64 rep_rows = getenv("SSRS_X_REPROWS") ? atoll(getenv("SSRS_X_REPROWS")) : 1000000;
     bool distributed = H.lv[0].parts.n > 1;
     for (int l = 0; l < 40; ++l) {
         Level& L = H.lv[(size_t)l];
