@@ -196,12 +196,22 @@ SSRS_HD inline double fine_apply64(const FineGraph& g, const FineWeights& W, int
     const int cols = g.cols;
     const i64 n = (i64)g.rows * cols;
     const i64 i = (i64)r * cols + c;
+    const double* w = W.wd;
+    if (r > 0 && r < g.rows - 1 && c > 0 && c < cols - 1) {
+        // interior cell (the quirk column is on the border): fixed offsets, same summation order as below
+        const double* wN = w + n; const double* wNE = w + 2 * n; const double* wNW = w + 3 * n;
+        const double xi = x[i];
+        double s = w[i] * (xi - x[i + 1]) + w[i - 1] * (xi - x[i - 1]);
+        s += wN[i] * (xi - x[i + cols]) + wN[i - cols] * (xi - x[i - cols]);
+        s += wNE[i] * (xi - x[i + cols + 1]) + wNE[i - cols - 1] * (xi - x[i - cols - 1]);
+        s += wNW[i] * (xi - x[i + cols - 1]) + wNW[i - cols + 1] * (xi - x[i - cols + 1]);
+        return s;
+    }
     const bool hW = c > 0, hE = c < cols - 1, hS = r > 0, hN = r < g.rows - 1;
     // a missing neighbour aliases the cell itself: its difference is exactly zero whatever weight is read
     const i64 jE = hE ? i + 1 : i, jW = hW ? i - 1 : i, jN = hN ? i + cols : i, jS = hS ? i - cols : i;
     const i64 jNE = (hN && hE) ? i + cols + 1 : i, jNW = (hN && hW) ? i + cols - 1 : i;
     const i64 jSW = (hS && hW) ? i - cols - 1 : i, jSE = (hS && hE) ? i - cols + 1 : i;
-    const double* w = W.wd;
     double wS = w[n + jS], wSW = w[2 * n + jSW];
     if (c == cols - 1 && hS && hN) {                                        // movmodel.py:73-79
         wS = link_weight<false>(g.kd[i], g.kd[jS], true);
@@ -471,6 +481,15 @@ template <class X>
 SSRS_HD inline real fine_apply32(const Fine32& F, int r, int c, const X& x) {
     const int cols = F.cols;
     const i64 i = (i64)r * cols + c;
+    if (r > 0 && r < F.rows - 1 && c > 0 && c < cols - 1) {
+        // interior cell (all but the raster's border; the quirk column is on the border): fixed offsets, same order
+        const real xi = x(i);
+        real s = F.wE[i] * (xi - x(i + 1)) + F.wE[i - 1] * (xi - x(i - 1));
+        s += F.wN[i] * (xi - x(i + cols)) + F.wN[i - cols] * (xi - x(i - cols));
+        s += F.wNE[i] * (xi - x(i + cols + 1)) + F.wNE[i - cols - 1] * (xi - x(i - cols - 1));
+        s += F.wNW[i] * (xi - x(i + cols - 1)) + F.wNW[i - cols + 1] * (xi - x(i - cols + 1));
+        return s;
+    }
     const bool hW = c > 0, hE = c < cols - 1, hS = r > 0, hN = r < F.rows - 1;
     // a missing neighbour aliases the cell itself: its difference is exactly zero whatever weight is read
     const i64 jE = hE ? i + 1 : i, jW = hW ? i - 1 : i, jN = hN ? i + cols : i, jS = hS ? i - cols : i;
