@@ -23,7 +23,11 @@ constructor always downloads terrain; here it is injected with keyword-only exte
     wind_points= (xlocs, ylocs) projected site coordinates (the reference's get_wtk_locs())
     bounds=      projected bounds (west, south, east, north); default puts the south-west corner at (0, 0)
 When `torch.distributed` is initialised, tracks are block-partitioned by global id over the ranks, fields are
-replicated and presence maps are summed with one all-reduce (NCCL on GPUs).
+replicated, the potential solve is row-sharded and presence maps are summed with one all-reduce (NCCL on GPUs).
+    case_parallel=True   instead distributes the wind CASES over the ranks (seasonal mode: rank r takes cases
+                 r, r + world, ...): every rank runs its cases exactly like a single-GPU run — no solver or presence
+                 communication — and only the summary presence map is reduced (the alternative to the
+                 row-sharded solve for seasonal throughput).
 """
 from __future__ import annotations
 
@@ -52,6 +56,33 @@ def _elapsed(t0: float) -> str:
     return f"{int(s // 60)} min {int(s % 60)} sec" if s >= 60 else f"{s:.2f} sec"
 
 
+class _SoloDist:
+    """`ssrs_b200.dist` as seen by one rank that owns whole cases (case_parallel mode): no sharding, no collectives."""
+
+    @staticmethod
+    def rank(): return 0
+
+    @staticmethod
+    def world_size(): return 1
+
+    @staticmethod
+    def barrier(): return None
+
+    @staticmethod
+    def agree(flag): return bool(flag)
+
+    shard_range = staticmethod(_dist.shard_range)
+
+    @staticmethod
+    def allreduce_sum(t): return t
+
+    @staticmethod
+    def presence_allreduce(t): return t
+
+    @staticmethod
+    def gather_tracks(tracks): return tracks
+
+
 class Simulator(Config):
     """ Class for SSRS simulation """
 
@@ -59,7 +90,7 @@ class Simulator(Config):
     time_format = 'y%Ym%md%dh%H'
 
     def __init__(self, in_config: Config = None, *, elevation=None, wind_cases: Optional[Dict] = None,
-                 wind_points=None, bounds=None, **kwargs) -> None:
+                 wind_points=None, bounds=None, case_parallel: bool = False, **kwargs) -> None:
         if in_config is None:
             super().__init__(**kwargs)
         else:
@@ -82,6 +113,9 @@ class Simulator(Config):
         with open(os.path.join(self.out_dir, self.run_name, f'{self.run_name}.json'), 'w', encoding='utf-8') as f:
             json.dump(self.__dict__, f, ensure_ascii=False, indent=2)
 
+        # per-case work sees `self._d`: the process group, or a single-process stand-in when cases are distributed
+        self._case_parallel = bool(case_parallel) and _dist.world_size() > 1
+        self._d = _SoloDist() if self._case_parallel else _dist
         print(f'Terrain resolution = {self.resolution} m')
         xsize = int(round((self.region_width_km[0] * 1000. / self.resolution)))
         ysize = int(round((self.region_width_km[1] * 1000. / self.resolution)))
@@ -127,12 +161,18 @@ class Simulator(Config):
             print(f'Uniform mode: Wind dirn = {self.uniform_winddirn} deg(cw)')
             self.case_ids = [self._get_uniform_id()]
             self.compute_orographic_updraft_uniform()
-        for case_id in self.case_ids:
+        for case_id in self._my_case_ids():
             self.compute_thermal_updrafts(case_id)
         fig_aspect = self.region_width_km[0] / self.region_width_km[1]
         self.fig_size = (self.fig_height * fig_aspect, self.fig_height)
         self.km_bar = min([1, 5, 10], key=lambda x: abs(x - self.region_width_km[0] // 4))
         print('SSRS Simulator initiation done.')
+
+    def _my_case_ids(self):
+        """Cases this rank computes: all of them, or every world-th one in case_parallel mode."""
+        if not self._case_parallel:
+            return list(self.case_ids)
+        return list(self.case_ids[_dist.rank()::_dist.world_size()])
 
     # ---------------------------------------------------------------- terrain
     def get_terrain_elevation(self):
@@ -155,9 +195,9 @@ class Simulator(Config):
 
     # ---------------------------------------------------------------- stage 1
     def _save_orograph(self, case_id, orograph):
-        if _dist.rank() == 0:
+        if self._d.rank() == 0:
             np.save(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy', orograph.cpu().numpy())
-        _dist.barrier()
+        self._d.barrier()
 
     def compute_orographic_updraft_uniform(self) -> None:
         print('Computing orographic updrafts..')
@@ -170,7 +210,7 @@ class Simulator(Config):
     def compute_orographic_updrafts_using_wtk(self) -> None:
         print('Computing orographic updrafts..', end="")
         t0 = time.time()
-        for case_id in self.case_ids:
+        for case_id in self._my_case_ids():
             ws, wd = self._wind_cases[case_id]
             if self._wind_points is not None and np.ndim(ws) == 1:
                 ws, wd = self._get_interpolated_wind_conditions(ws, wd)
@@ -195,9 +235,9 @@ class Simulator(Config):
             for real_id in range(self.thermals_realization_count):
                 seed = None if self.sim_seed < 0 else (self.sim_seed * 7919 + ci * 104729 + real_id + 1)
                 thermals = compute_thermals(aspect, 2.0, seed=seed)
-                if _dist.rank() == 0:
+                if self._d.rank() == 0:
                     np.save(f'{self._get_thermal_fname(case_id, real_id, self.mode_data_dir)}.npy', thermals.cpu().numpy())
-            _dist.barrier()
+            self._d.barrier()
         else:
             print('No thermals requested!', flush=True)
 
@@ -230,7 +270,7 @@ class Simulator(Config):
         fname = self._get_potential_fname(case_id, real_id, self.mode_data_dir)
         id_str = self._get_id_string(case_id, real_id)
         try:
-            if not _dist.agree(os.path.exists(f'{fname}.npy')):
+            if not self._d.agree(os.path.exists(f'{fname}.npy')):
                 raise FileNotFoundError         # the solve is collective: all ranks follow rank 0's view of the cache
             potential = np.load(f'{fname}.npy')
             if potential.shape != self.gridsize:
@@ -243,14 +283,14 @@ class Simulator(Config):
             t0 = time.time()
             print(f'{id_str}: Computing potential..', end="", flush=True)
             pot_dev, stats = solve_potential_device(updraft, self.track_direction, strict=False,
-                                                    sharded=_dist.world_size() > 1)       # row-sharded over the ranks
+                                                    sharded=self._d.world_size() > 1)       # row-sharded over the ranks
             self.timings['potential_s'] = time.time() - t0
             self.solve_stats = stats
             print(f'took {_elapsed(t0)}', flush=True)
             potential = pot_dev.cpu().numpy()
-            if _dist.rank() == 0:
+            if self._d.rank() == 0:
                 np.save(f'{fname}.npy', potential)
-            _dist.barrier()
+            self._d.barrier()
         if np.isnan(potential).any():
             print('NANs found in potential!')
         self._last_potential_device = pot_dev
@@ -280,9 +320,10 @@ class Simulator(Config):
         starting_rows, starting_cols = get_starting_indices(
             self.track_count, self.track_start_region, self.track_start_type, self.region_width_km, self.resolution)
         n = len(starting_rows)
-        lo, hi = _dist.shard_range(n, _dist.rank(), _dist.world_size())
+        lo, hi = self._d.shard_range(n, self._d.rank(), self._d.world_size())
         record = (n <= TRACKS_PKL_LIMIT) if save_tracks is None else bool(save_tracks)
-        for ci, case_id in enumerate(self.case_ids):
+        for case_id in self._my_case_ids():
+            ci = self.case_ids.index(case_id)
             for real_id, updraft in enumerate(self._load_updrafts_device(case_id)):
                 if self.sim_seed > 0:
                     np.random.seed(self.sim_seed + real_id)              # reference :351-352
@@ -299,8 +340,8 @@ class Simulator(Config):
                                             self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
                                             fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
                                             record=record)
-                presence = _dist.presence_allreduce(res.presence)        # ssrs_presence_allreduce (NCCL) when world > 1
-                steps = _dist.allreduce_sum(res._total.clone())
+                presence = self._d.presence_allreduce(res.presence)        # ssrs_presence_allreduce (NCCL) when world > 1
+                steps = self._d.allreduce_sum(res._total.clone())
                 torch.cuda.synchronize()
                 self.timings['tracks_s'] = time.time() - t0
                 self.total_track_steps = int(steps.item())
@@ -309,15 +350,15 @@ class Simulator(Config):
                 fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
                 if record and n <= TRACKS_PKL_LIMIT:
                     tracks = res.tracks()
-                    tracks = _dist.gather_tracks(tracks)
-                    if _dist.rank() == 0:
+                    tracks = self._d.gather_tracks(tracks)
+                    if self._d.rank() == 0:
                         trackio.save_tracks_pickle(fname, tracks)        # the reference's file (:383-386)
                 elif record:
                     # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
                     off, pts = res.packed()
-                    suffix = '' if _dist.world_size() == 1 else f'_part{_dist.rank()}of{_dist.world_size()}'
+                    suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
                     trackio.save_tracks_packed(f'{fname}{suffix}', off, pts)
-                if not record and _dist.rank() == 0:
+                if not record and self._d.rank() == 0:
                     np.savez_compressed(f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
 
     def load_tracks(self, case_id: Optional[str] = None, real_id: int = 0):
@@ -329,7 +370,11 @@ class Simulator(Config):
     def presence_counts(self, case_id: Optional[str] = None, real_id: int = 0) -> np.ndarray:
         """int32 visit counts of the last simulate_tracks() (reference compute_presence_counts, movmodel.py:410-419)."""
         case_id = self.case_ids[0] if case_id is None else case_id
-        return self._presence[self._get_id_string(case_id, real_id)].cpu().numpy()
+        key = self._get_id_string(case_id, real_id)
+        if key not in self._presence:
+            raise KeyError(f"no presence counts for {key} on this rank (not simulated yet, or owned by another rank "
+                           f"in case_parallel mode)")
+        return self._presence[key].cpu().numpy()
 
     def _get_tracks_fname(self, case_id: str, real_id: int, dirname: str):
         return os.path.join(dirname, f'{self._get_id_string(case_id, real_id)}_tracks')
@@ -343,7 +388,7 @@ class Simulator(Config):
         from .presence import smooth_presence_counts
         krad = min(max(radius / self.resolution, 2), min(self.gridsize) / 2)
         summary = None
-        for case_id in self.case_ids:
+        for case_id in self._my_case_ids():
             case_prob = None
             for real_id in range(1 + int(self.thermals_realization_count)):
                 counts = self._presence[self._get_id_string(case_id, real_id)]
@@ -352,6 +397,11 @@ class Simulator(Config):
                 case_prob = pr if case_prob is None else case_prob + pr
             case_prob = case_prob / case_prob.max()
             summary = case_prob if summary is None else summary + case_prob
+        if self._case_parallel:                 # the only exchange of this mode: sum of the ranks' case maps
+            torch = N.require_cuda()
+            if summary is None:                 # more ranks than cases
+                summary = torch.zeros(self.gridsize, dtype=torch.float32, device="cuda")
+            summary = _dist.allreduce_sum(summary.float().contiguous())
         summary = (summary / summary.max()).float().cpu().numpy()
         if _dist.rank() == 0:
             np.save(os.path.join(self.mode_data_dir, 'summary_presence.npy'), summary)

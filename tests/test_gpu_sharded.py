@@ -26,3 +26,19 @@ def test_sharded_solve_two_gpus():
     assert out["sharded"]["converged"] in (1, 2)
     assert out["max_abs_diff_vs_single"] <= 2 * float(np.spacing(np.float32(1000.0)))     # float32-rounding level
     assert out["identical_on_all_ranks"] and out["presence_allreduce_ok"]
+
+
+@pytest.mark.gpu
+def test_seasonal_sharded_vs_case_parallel_two_gpus():
+    """Seasonal mode on 2 GPUs, both ways of using them: every case sharded over the ranks vs the cases
+    distributed over the ranks.  Same seeds -> bit-identical per-case presence counts and the same summary map."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29500 + (os.getpid() + 7) % 400
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "seasonal_run.py"), "400", "480", "100", "4", "2000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["same_counts_per_case"] and out["same_summary"]
