@@ -359,7 +359,7 @@ class Simulator(Config):
                     suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
                     trackio.save_tracks_packed(f'{fname}{suffix}', off, pts)
                 if not record and self._d.rank() == 0:
-                    np.savez_compressed(f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
+                    np.savez(f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())     # (compression of a 120 MB raster costs seconds)
 
     def load_tracks(self, case_id: Optional[str] = None, real_id: int = 0):
         """The stored tracks of (case, realisation) as the reference's list of int16 [L, 2] arrays, from either
