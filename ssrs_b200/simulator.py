@@ -56,6 +56,24 @@ def _elapsed(t0: float) -> str:
     return f"{int(s // 60)} min {int(s % 60)} sec" if s >= 60 else f"{s:.2f} sec"
 
 
+class _ArtefactWriter:
+    """Background writer for the on-disk artefacts (.npy/.npz/.pkl): a 120 MB raster takes longer to write than the GPU
+    takes to produce the next one, and numpy releases the GIL while writing.  `wait()` before anything reads them."""
+
+    def __init__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=2)
+        self._pending = []
+
+    def submit(self, fn, *args, **kwargs):
+        self._pending.append(self._pool.submit(fn, *args, **kwargs))
+
+    def wait(self):
+        pending, self._pending = self._pending, []
+        for f in pending:
+            f.result()              # re-raises a failed write
+
+
 class _SoloDist:
     """`ssrs_b200.dist` as seen by one rank that owns whole cases (case_parallel mode): no sharding, no collectives."""
 
@@ -140,6 +158,8 @@ class Simulator(Config):
         if tuple(z.shape) != self.gridsize:
             raise ValueError(f"elevation shape {tuple(z.shape)} does not match gridsize {self.gridsize}")
         self._elev = z
+        self._writer = _ArtefactWriter()
+        self._oro_cache: Dict[str, "torch.Tensor"] = {}       # float32 orographs kept on the device (what the .npy holds)
         self._presence: Dict[str, "torch.Tensor"] = {}
         self._track_results = {}
         self.timings: Dict[str, float] = {}
@@ -166,6 +186,7 @@ class Simulator(Config):
         fig_aspect = self.region_width_km[0] / self.region_width_km[1]
         self.fig_size = (self.fig_height * fig_aspect, self.fig_height)
         self.km_bar = min([1, 5, 10], key=lambda x: abs(x - self.region_width_km[0] // 4))
+        self.flush()             # the constructor's artefacts (orographs, thermals) are on disk when it returns
         print('SSRS Simulator initiation done.')
 
     def _my_case_ids(self):
@@ -194,9 +215,22 @@ class Simulator(Config):
         return xgrid, ygrid
 
     # ---------------------------------------------------------------- stage 1
+    ORO_CACHE_BYTES = 32 << 30          # device budget for cached orographs (64 cases x 480 MB at 12000 x 10000 = 31 GB)
+
     def _save_orograph(self, case_id, orograph):
+        """`<case>_orograph.npy` (float32, reference :197-198), written in the background; the device copy is kept
+        so that load_updrafts' float32 round trip through the file (reference :232-233) costs nothing."""
         if self._d.rank() == 0:
-            np.save(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy', orograph.cpu().numpy())
+            self._writer.submit(np.save, f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy', orograph.cpu().numpy())
+        if orograph.numel() * 4 * len(self.case_ids) <= self.ORO_CACHE_BYTES:
+            self._oro_cache[case_id] = orograph
+        else:
+            self._writer.wait()
+            self._d.barrier()
+
+    def flush(self):
+        """Blocks until every artefact of this Simulator is on disk (collective when torch.distributed is initialised)."""
+        self._writer.wait()
         self._d.barrier()
 
     def compute_orographic_updraft_uniform(self) -> None:
@@ -247,7 +281,9 @@ class Simulator(Config):
 
     def _load_updrafts_device(self, case_id, apply_threshold=True):
         torch = N.require_cuda()
-        oro = torch.from_numpy(np.load(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy')).to("cuda")
+        oro = self._oro_cache.get(case_id)
+        if oro is None:
+            oro = torch.from_numpy(np.load(f'{self._get_orograph_fname(case_id, self.mode_data_dir)}.npy')).to("cuda")
         updrafts = [oro]
         for real_id in range(int(self.thermals_realization_count)):
             th = np.load(f'{self._get_thermal_fname(case_id, real_id, self.mode_data_dir)}.npy')
@@ -289,8 +325,7 @@ class Simulator(Config):
             print(f'took {_elapsed(t0)}', flush=True)
             potential = pot_dev.cpu().numpy()
             if self._d.rank() == 0:
-                np.save(f'{fname}.npy', potential)
-            self._d.barrier()
+                self._writer.submit(np.save, f'{fname}.npy', potential)
         if np.isnan(potential).any():
             print('NANs found in potential!')
         self._last_potential_device = pot_dev
@@ -352,14 +387,16 @@ class Simulator(Config):
                     tracks = res.tracks()
                     tracks = self._d.gather_tracks(tracks)
                     if self._d.rank() == 0:
-                        trackio.save_tracks_pickle(fname, tracks)        # the reference's file (:383-386)
+                        self._writer.submit(trackio.save_tracks_pickle, fname, tracks)        # the reference's file (:383-386)
                 elif record:
                     # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
                     off, pts = res.packed()
                     suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
-                    trackio.save_tracks_packed(f'{fname}{suffix}', off, pts)
+                    self._writer.submit(trackio.save_tracks_packed, f'{fname}{suffix}', off, pts)
                 if not record and self._d.rank() == 0:
-                    np.savez(f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())     # (compression of a 120 MB raster costs seconds)
+                    # (uncompressed: compressing a 120 MB raster costs seconds)
+                    self._writer.submit(np.savez, f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
+        self.flush()
 
     def load_tracks(self, case_id: Optional[str] = None, real_id: int = 0):
         """The stored tracks of (case, realisation) as the reference's list of int16 [L, 2] arrays, from either
