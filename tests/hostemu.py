@@ -4,6 +4,7 @@ The product package never loads this library."""
 import ctypes as C
 import os
 import subprocess
+import zlib
 
 import numpy as np
 
@@ -21,11 +22,16 @@ class Stats(C.Structure):
 
 
 def build():
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-DSSRS_HOST_EMU", "-x", "c++", "-shared", "-fPIC", "-o", OUT, SRC],
+    """SSRS_EMU_FLAGS (e.g. "-fsanitize=address -g -O1", run with LD_PRELOAD=libasan.so) builds a separate library."""
+    extra = os.environ.get("SSRS_EMU_FLAGS", "").split()
+    out = OUT if not extra else OUT.replace(".so", f"_{zlib.crc32(' '.join(extra).encode()):08x}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
+        tmp = f"{out}.{os.getpid()}.tmp"                    # concurrent ranks may build at the same time
+        subprocess.run(["g++", "-O2", "-std=c++17", "-DSSRS_HOST_EMU", *extra, "-x", "c++", "-shared", "-fPIC", "-o", tmp, SRC],
                        check=True)
-    return OUT
+        os.replace(tmp, out)
+    return out
 
 
 _lib = None
