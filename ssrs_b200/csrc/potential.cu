@@ -521,21 +521,28 @@ inline int fine_first32(const Fine32 F, int r0, int r1, const double* b, real* x
         x[i] = omega * F.dinv[i] * (real)b[i];
     });
 }
+// (No early exit on Dirichlet cells in these kernels: a branch on a loaded value in front of the stencil would put
+// one more memory latency on every cell's critical path.  The stencil is safe to evaluate there; the result is
+// discarded by a select.)
 // x = first sweep, res = b - A x in one pass over b
 inline int fine_first_residual32(const Fine32 F, int r0, int r1, const double* b, real* x, real* res, real omega, stream_t st) {
     return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
-        if (F.dinv[i] == 0.0f) { x[i] = (real)0.0; res[i] = (real)0.0; return; }
         const FirstSweepFine x1 = {b, F.dinv, omega};
-        x[i] = x1(i);
-        res[i] = (real)b[i] - fine_apply32(F, r, c, x1);
+        const bool free_node = F.dinv[i] != 0.0f;
+        const real bi = (real)b[i];
+        const real ax = fine_apply32(F, r, c, x1);
+        x[i] = x1(i);                                   // 0 at Dirichlet cells (dinv = 0)
+        res[i] = free_node ? bi - ax : (real)0.0;
     });
 }
 inline int fine_residual32(const Fine32 F, int r0, int r1, const double* b, const real* x, real* res, stream_t st) {
     return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
-        if (F.dinv[i] == 0.0f) { res[i] = (real)0.0; return; }
-        res[i] = (real)b[i] - fine_apply32(F, r, c, VecF{x});
+        const bool free_node = F.dinv[i] != 0.0f;
+        const real bi = (real)b[i];
+        const real ax = fine_apply32(F, r, c, VecF{x});
+        res[i] = free_node ? bi - ax : (real)0.0;
     });
 }
 template <class OutT>
@@ -543,8 +550,9 @@ inline int fine_jacobi32(const Fine32 F, int r0, int r1, const double* b, const 
     return pfor2d_rows(r0, r1, F.cols, st, [=] SSRS_HD(int r, int c) {
         const i64 i = (i64)r * F.cols + c;
         const real di = F.dinv[i];
-        if (di == (real)0.0) { xn[i] = (OutT)0; return; }
-        xn[i] = (OutT)(x[i] + omega * di * ((real)b[i] - fine_apply32(F, r, c, VecF{x})));
+        const real bi = (real)b[i];
+        const real ax = fine_apply32(F, r, c, VecF{x});
+        xn[i] = (di == (real)0.0) ? (OutT)0 : (OutT)(x[i] + omega * di * (bi - ax));
     });
 }
 
@@ -909,7 +917,9 @@ int fine_residual(const FineGraph fg, const FineWeights W, int r0, int r1, const
     double dummy;
     AMG_TRY(preduce2d_sum2_rows(r0, r1, fg.cols, st, nrm2, &dummy, [=] SSRS_HD(int r, int c, double& u0, double& u1) {
         const i64 i = (i64)r * fg.cols + c;
-        const double v = fg.excluded(i) ? 0.0 : -fine_apply64(fg, W, r, c, x);
+        const bool free_node = !fg.excluded(i);
+        const double ax = fine_apply64(fg, W, r, c, x);
+        const double v = free_node ? -ax : 0.0;
         out[i] = v;
         u0 = v * v; u1 = 0.0;
     }));
@@ -920,9 +930,12 @@ int fine_apply_dots(const FineGraph fg, const FineWeights W, int r0, int r1, con
                     double* d0, double* d1, stream_t st) {
     AMG_TRY(preduce2d_sum2_rows(r0, r1, fg.cols, st, d0, d1, [=] SSRS_HD(int r, int c, double& u0, double& u1) {
         const i64 i = (i64)r * fg.cols + c;
-        const double v = fg.excluded(i) ? 0.0 : fine_apply64(fg, W, r, c, in);
+        const bool free_node = !fg.excluded(i);
+        const double wi = w0[i];                       // (issued with the stencil's loads, not after them)
+        const double ax = fine_apply64(fg, W, r, c, in);
+        const double v = free_node ? ax : 0.0;
         out[i] = v;
-        u0 = w0[i] * v; u1 = v * v;
+        u0 = wi * v; u1 = v * v;
     }));
     return SSRS_OK;
 }
