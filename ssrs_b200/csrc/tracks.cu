@@ -47,18 +47,20 @@ struct TrackParams {
     double nu;
     double max_moves;
     int rows, cols, burnin, memory, nu_is_one, kmax;
+    unsigned rk[20];                      // Philox round keys (seed + i * Weyl constants), formed once on the host
 };
 
 // Philox4x32-10 (Salmon et al. 2011), counter = (track_lo, track_hi, step_lo, step_hi), key = seed.
-__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                              unsigned k1, unsigned& o0, unsigned& o1, unsigned& o2, unsigned& o3) {
+// The ten round keys (k0 + i * 0x9E3779B9, k1 + i * 0xBB67AE85) are the same for every block of a launch: they sit in
+// the kernel parameters, where the xor reads them as constant-bank operands (no key-schedule instructions).
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, const TrackParams& P,
+                                              unsigned& o0, unsigned& o1, unsigned& o2, unsigned& o3) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        unsigned n0 = hi1 ^ c1 ^ P.rk[2 * i], n1 = lo1, n2 = hi0 ^ c3 ^ P.rk[2 * i + 1], n3 = lo0;
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
@@ -251,18 +253,104 @@ __device__ __forceinline__ int choose_fast3(const TrackParams& P, const float2* 
     return q2 > 0.0 ? i2 : (q1 > 0.0 ? i1 : i0);
 }
 
+// Out-of-line copy of the three-candidate step for the fast lane's rare cases (see fast_step).
+__device__ __noinline__ int choose_fast3_rare(const TrackParams& P, const float2* base, int nc, int i0, int i1, int i2,
+                                              float2 fc, float2 f0, float2 f1, float2 f2, double u) {
+    return choose_fast3<true, true>(P, base, nc, 0u, i0, i1, i2, fc, f0, f1, f2, u);
+}
+
+__device__ __forceinline__ float fmax_nan(float a, float b) {      // NaN if either operand is NaN
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+__device__ __forceinline__ void red_add1(unsigned* p) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+// Fast-lane tables, one row per previous move.  Rows are indexed by the move's "slot" = flat index with the centre
+// (4) squeezed out, 0..7, so that eight rows of 16 bytes cover the 32 shared-memory banks exactly once: lanes of a warp
+// that hold different previous moves read their rows without bank conflicts.
+struct FastLut {
+    int4 cand[8];       // element offsets of the three candidates from the centre cell; .w = their slots, 4 bits each
+    float4 ninv[8];     // float32(1/sqrt 2) for diagonal candidates, else 1 (movmodel.py:139-141)
+    double2 dir01[8];   // directional weights of candidates 0 and 1 (the fallback of movmodel.py:234-236)
+    double dir2[8];     // ... and of candidate 2
+};
+__device__ __forceinline__ unsigned slot_of(unsigned flat) { return flat - (flat > 4u ? 1u : 0u); }
+__device__ __forceinline__ unsigned flat_of(unsigned slot) { return slot + (slot >= 4u ? 1u : 0u); }
+
+// One fast-lane step: choose_fast3<true, true> with the selection made branch-free and the new centre's fields taken
+// from the chosen candidate's registers instead of a fourth gather.
+//   * d_i NaN or no d_i > 0  <=>  choose_fast3's (any_nan || all q == 0): the weights become the directional ones
+//     (q_i == 0 exactly when d_i <= 0, because the clipped updrafts are >= 1e-6);
+//   * max(d_i, 0) replaces `d_i > 0 ? ... : 0`: the product is the same for d_i > 0 and a zero otherwise;
+//   * when c2 > target the chosen move is the first running sum above the target — the same three comparisons; every
+//     other case (weights all zero after the fallback, u * c2 rounding up to c2, a NaN or infinite updraft) goes to
+//     the out-of-line copy of the original code.  Same draws, same arithmetic: bit-identical trajectories.
+__device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& lut, int nc, int& lin, unsigned& slot,
+                                          float2& fc, double& uc, double u) {
+    const int4 cand = lut.cand[slot];
+    const float4 nv = lut.ninv[slot];
+    // 32-bit cell indices (rows * cols < 2^31): one IMAD.WIDE per address
+    const float2 f0 = __ldg(P.fields + (lin + cand.x)), f1 = __ldg(P.fields + (lin + cand.y)), f2 = __ldg(P.fields + (lin + cand.z));
+    const double2 dir01 = lut.dir01[slot];
+    const double dir2 = lut.dir2[slot];
+    const float d0 = __fmul_rn(__fsub_rn(fc.y, f0.y), nv.x);            // float32, movmodel.py:301-304
+    const float d1 = __fmul_rn(__fsub_rn(fc.y, f1.y), nv.y);
+    const float d2 = __fmul_rn(__fsub_rn(fc.y, f2.y), nv.z);
+    const bool use_dir = !(fmax_nan(fmax_nan(d0, d1), d2) > 0.0f);
+    const double u0 = clip_updraft(f0.x), u1 = clip_updraft(f1.x), u2 = clip_updraft(f2.x);
+    const double s0 = uc + u0, s1 = uc + u1, s2 = uc + u2;
+    double q0 = ((double)fmaxf(d0, 0.0f) * u0) * (s1 * s2);
+    double q1 = ((double)fmaxf(d1, 0.0f) * u1) * (s0 * s2);
+    double q2 = ((double)fmaxf(d2, 0.0f) * u2) * (s0 * s1);
+    if (use_dir) { q0 = dir01.x; q1 = dir01.y; q2 = dir2; }
+    const double c1 = q0 + q1, c2 = c1 + q2;
+    const double target = u * c2;
+    if (c2 > target) {
+        const bool a = q0 > target, b = c1 > target;
+        lin += a ? cand.x : (b ? cand.y : cand.z);
+        slot = ((unsigned)cand.w >> (a ? 0 : (b ? 4 : 8))) & 15u;
+        fc = a ? f0 : (b ? f1 : f2);
+        uc = a ? u0 : (b ? u1 : u2);
+    } else {
+        const int idx = choose_fast3_rare(P, P.fields + lin, nc, (int)flat_of(cand.w & 15), (int)flat_of((cand.w >> 4) & 15),
+                                          (int)flat_of((cand.w >> 8) & 15), fc, f0, f1, f2, u);
+        const int dr = ((idx * 11) >> 5) - 1, dc = idx - 3 * (dr + 1) - 1;
+        lin += dr * nc + dc;
+        slot = slot_of((unsigned)idx);
+        fc = __ldg(P.fields + lin);
+        uc = clip_updraft(fc.x);
+    }
+    red_add1(P.presence + lin);
+}
+
 // MEM1: track_dirn_restrict == 1 (the default): the mask is exactly the three candidates of the last move, so
 // no history register, no mask arithmetic.
 template <bool HAS_FIELDS, bool EXACT, bool MEM1>
 __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P) {
-    // per previous move: element offsets of its three candidates and their packed flat indices
-    __shared__ int4 s_cand[9];
+    // per previous move: element offsets of its three candidates, their packed indices, distance factors and
+    // directional weights
+    __shared__ int4 s_cand[9];                 // general step: indexed by the flat move index, .w = flat indices
+    __shared__ FastLut s_lut;                  // fast lane: indexed by slot
     if (threadIdx.x < 9) {
         const unsigned last = threadIdx.x;
         const unsigned c3 = (unsigned)((last < 5 ? (C3_A >> (12 * last)) : (C3_B >> (12 * (last - 5)))) & 0xFFFu);
         const int i0 = c3 & 15, i1 = (c3 >> 4) & 15, i2 = (c3 >> 8) & 15;
-        s_cand[last] = make_int4((i0 / 3 - 1) * P.cols + (i0 % 3 - 1), (i1 / 3 - 1) * P.cols + (i1 % 3 - 1),
-                                 (i2 / 3 - 1) * P.cols + (i2 % 3 - 1), (int)c3);
+        const int4 off = make_int4((i0 / 3 - 1) * P.cols + (i0 % 3 - 1), (i1 / 3 - 1) * P.cols + (i1 % 3 - 1),
+                                   (i2 / 3 - 1) * P.cols + (i2 % 3 - 1), (int)c3);
+        s_cand[last] = off;
+        if (last != 4u) {
+            const unsigned sl = slot_of(last);
+            s_lut.cand[sl] = make_int4(off.x, off.y, off.z, (int)(slot_of(i0) | (slot_of(i1) << 4) | (slot_of(i2) << 8)));
+            // even flat index (0,2,6,8) = diagonal move
+            s_lut.ninv[sl] = make_float4((i0 & 1) ? 1.0f : 0.70710677f, (i1 & 1) ? 1.0f : 0.70710677f,
+                                         (i2 & 1) ? 1.0f : 0.70710677f, 0.f);
+            s_lut.dir01[sl] = make_double2(P.dirp[i0], P.dirp[i1]);
+            s_lut.dir2[sl] = P.dirp[i2];
+        }
     }
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -290,34 +378,37 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
         }
         // Fast lane: pairs of ordinary steps (interior cell, previous move known, nu == 1, Philox stream, counts only,
         // no trajectory store) run in a tight loop without the bookkeeping below; one Philox block feeds both steps
-        // of a pair, so there is no parity branch.  Anything else — first step, burn-in relocation or exit near the
-        // border, the move limit — leaves the loop and takes the general step.  Same arithmetic, same draws.
+        // of a pair, so there is no parity branch.  The loop carries the linear cell index only: a track whose
+        // distance to the nearest non-interior cell is m cannot leave the interior in m steps, so it takes
+        // floor((m + 1) / 2) pairs without looking at the border and then measures the distance again.  Anything
+        // else — first step, burn-in relocation or exit near the border, the move limit — leaves the loop and takes
+        // the general step.  Same arithmetic, same draws.
         if (HAS_FIELDS && !EXACT && MEM1 && fast_lane && last != 4u && (k & 1) == 0) {
             const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
-            while (row > 1 && row < nr - 2 && col > 0 && col < nc - 2 && k + 1 < kmax) {
+            const unsigned g0 = (unsigned)gid, g1 = (unsigned)(gid >> 32);
+            int lin = row * nc + col;
+            unsigned kp = (unsigned)k >> 1;
+            unsigned slot = slot_of(last);
+            int budget = 0;
+            float2 fc = make_float2(0.f, 0.f);
+            double uc = 0.0;
+            bool have_centre = false;
+            while (true) {
+                if (budget == 0) {
+                    row = lin / nc; col = lin - row * nc;
+                    const int m = min(min(row - 2, nr - 3 - row), min(col - 1, nc - 3 - col));
+                    budget = min((m + 1) >> 1, (kmax - (int)(2u * kp)) >> 1);
+                    if (budget <= 0) break;
+                    if (!have_centre) { fc = __ldg(P.fields + lin); uc = clip_updraft(fc.x); have_centre = true; }
+                }
                 unsigned a, b, cc, dd;
-                int lin = row * nc + col;
-                const float2* base = P.fields + lin;
-                int4 cand = s_cand[last];
-                float2 fc = __ldg(base), f0 = __ldg(base + cand.x), f1 = __ldg(base + cand.y), f2 = __ldg(base + cand.z);
-                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, (unsigned)P.seed,
-                              (unsigned)(P.seed >> 32), a, b, cc, dd);
-                int idx = choose_fast3<true, true>(P, base, nc, 0u, cand.w & 15, (cand.w >> 4) & 15, (cand.w >> 8) & 15,
-                                                   fc, f0, f1, f2, uniform52(a, b));
-                int dr = ((idx * 11) >> 5) - 1, dc = idx - 3 * (dr + 1) - 1;
-                row += dr; col += dc; ++k; last = (unsigned)idx;
-                atomicAdd(P.presence + (lin + dr * nc + dc), 1u);
-                if (!(row > 1 && row < nr - 2 && col > 0 && col < nc - 2)) { rng_c = cc; rng_d = dd; break; }
-                lin = row * nc + col;
-                base = P.fields + lin;
-                cand = s_cand[last];
-                fc = __ldg(base); f0 = __ldg(base + cand.x); f1 = __ldg(base + cand.y); f2 = __ldg(base + cand.z);
-                idx = choose_fast3<true, true>(P, base, nc, 0u, cand.w & 15, (cand.w >> 4) & 15, (cand.w >> 8) & 15,
-                                               fc, f0, f1, f2, uniform52(cc, dd));
-                dr = ((idx * 11) >> 5) - 1; dc = idx - 3 * (dr + 1) - 1;
-                row += dr; col += dc; ++k; last = (unsigned)idx;
-                atomicAdd(P.presence + (lin + dr * nc + dc), 1u);
+                philox4x32_10(g0, g1, kp, 0u, P, a, b, cc, dd);
+                fast_step(P, s_lut, nc, lin, slot, fc, uc, uniform52(a, b));
+                fast_step(P, s_lut, nc, lin, slot, fc, uc, uniform52(cc, dd));
+                ++kp; --budget;
             }
+            k = (int)(2u * kp);
+            last = flat_of(slot);
         }
         int r = row, c = col;
         bool finish = k >= kmax;                                            // movmodel.py:285
@@ -369,8 +460,7 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
             if ((k & 1) == 0) {
                 const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
                 unsigned a, b;
-                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, (unsigned)P.seed,
-                              (unsigned)(P.seed >> 32), a, b, rng_c, rng_d);
+                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, P, a, b, rng_c, rng_d);
                 u = uniform52(a, b);
             } else {
                 u = uniform52(rng_c, rng_d);
@@ -470,6 +560,10 @@ extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const i
     P.rows = rows; P.cols = cols;
     P.burnin = (int)((rows < cols ? rows : cols) / 10);                      // movmodel.py:276
     P.memory = memory;
+    for (int i = 0; i < 10; ++i) {
+        P.rk[2 * i] = (unsigned)seed + (unsigned)i * 0x9E3779B9u;
+        P.rk[2 * i + 1] = (unsigned)(seed >> 32) + (unsigned)i * 0xBB67AE85u;
+    }
     // verification mode always uses the exact (numpy bit-for-bit) arithmetic
     const bool exact = (uniforms != nullptr) || (flags & SSRS_STEP_EXACT);
     const int threads = 128;
