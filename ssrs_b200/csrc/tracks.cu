@@ -18,6 +18,8 @@
 
 #include <math.h>
 
+#include <mutex>
+
 namespace ssrs {
 namespace {
 
@@ -41,6 +43,7 @@ struct TrackParams {
     int* traj_len;
     unsigned* presence;
     unsigned long long* total_steps;
+    unsigned long long* next_track;       // device counter, zero at launch: tracks beyond the first per thread are drawn from it
     long long n_tracks, track_id0, ustride, traj_cap;
     unsigned long long seed;
     double dirp[9];
@@ -277,6 +280,8 @@ struct FastLut {
     float4 ninv[8];     // float32(1/sqrt 2) for diagonal candidates, else 1 (movmodel.py:139-141)
     double2 dir01[8];   // directional weights of candidates 0 and 1 (the fallback of movmodel.py:234-236)
     double dir2[8];     // ... and of candidate 2
+    double drun[9];     // running sums of the nine directional weights in flat order (the unmasked fallback, :239-240)
+    int dlast;          // last flat index with a positive directional weight (4 if none)
 };
 __device__ __forceinline__ unsigned slot_of(unsigned flat) { return flat - (flat > 4u ? 1u : 0u); }
 __device__ __forceinline__ unsigned flat_of(unsigned slot) { return slot + (slot >= 4u ? 1u : 0u); }
@@ -316,8 +321,21 @@ __device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& l
         fc = a ? f0 : (b ? f1 : f2);
         uc = a ? u0 : (b ? u1 : u2);
     } else {
-        const int idx = choose_fast3_rare(P, P.fields + lin, nc, (int)flat_of(cand.w & 15), (int)flat_of((cand.w >> 4) & 15),
-                                          (int)flat_of((cand.w >> 8) & 15), fc, f0, f1, f2, u);
+        int idx;
+        if (use_dir && c2 == 0.0) {
+            // the candidates' directional weights are zero as well (a track heading away from track_direction in a
+            // potential minimum, ~1 % of all steps): the reference drops the mask and draws from all nine directional
+            // weights (movmodel.py:239-240).  That distribution does not depend on the cell: first flat index whose
+            // running sum exceeds u * total, exactly what choose_fast_general<false>(mask 0) evaluates.
+            const double tg = u * lut.drun[8];
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) cnt += (lut.drun[i] > tg) ? 0 : 1;       // running sums are non-decreasing
+            idx = cnt < 9 ? cnt : lut.dlast;
+        } else {
+            idx = choose_fast3_rare(P, P.fields + lin, nc, (int)flat_of(cand.w & 15), (int)flat_of((cand.w >> 4) & 15),
+                                    (int)flat_of((cand.w >> 8) & 15), fc, f0, f1, f2, u);
+        }
         const int dr = ((idx * 11) >> 5) - 1, dc = idx - 3 * (dr + 1) - 1;
         lin += dr * nc + dc;
         slot = slot_of((unsigned)idx);
@@ -350,6 +368,15 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
                                          (i2 & 1) ? 1.0f : 0.70710677f, 0.f);
             s_lut.dir01[sl] = make_double2(P.dirp[i0], P.dirp[i1]);
             s_lut.dir2[sl] = P.dirp[i2];
+        } else {
+            double run = 0.0;
+            int lastpos = 4;
+            for (int i = 0; i < 9; ++i) {                       // same order of additions as choose_fast_general
+                run += P.dirp[i];
+                s_lut.drun[i] = run;
+                if (P.dirp[i] > 0.0) lastpos = i;
+            }
+            s_lut.dlast = lastpos;
         }
     }
     __syncthreads();
@@ -365,127 +392,152 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
     int hcount = 1;
     unsigned run_mask = 0x1EF;            // AND over the whole history (memory == 0)
     unsigned rng_c = 0, rng_d = 0;        // second half of the last Philox block
-    const bool fast_lane = P.nu_is_one && P.uniforms == nullptr && P.traj == nullptr && P.presence != nullptr;
+    // Fast lane: pairs of ordinary steps (interior cell, previous move known, nu == 1, Philox stream, counts only, no
+    // trajectory store) without the general step's bookkeeping; one Philox block feeds both steps of a pair, so there is
+    // no parity branch.  The fast lane carries the linear cell index only: a track whose distance to the nearest
+    // non-interior cell is m cannot leave the interior in m steps, so it is granted floor((m + 1) / 2) pairs ("budget")
+    // without looking at the border and then measures the distance again.  Same arithmetic, same draws.
+    const bool fast_lane = HAS_FIELDS && !EXACT && MEM1 && P.nu_is_one && P.uniforms == nullptr && P.traj == nullptr &&
+                           P.presence != nullptr;
+    // While a lane has budget its state lives in the same registers in fast-lane form: `row` holds the linear cell index,
+    // `k` the pair counter k / 2, `last` the previous move's slot (the kernel sits at the register limit of 6 CTAs/SM).
+    bool done = false, in_fast = false;
+    int budget = 0;
+    float2 fcen = make_float2(0.f, 0.f);
+    double ucen = 0.0;
 
+    // One flat loop, two blocks per iteration: the attention block (a lane without budget: refill, budget refresh, or
+    // one general step) and the pair block (lanes with budget).  Both reconverge inside the iteration, so a lane whose
+    // track has ended waits at most one block for its warp before it starts the next track — with an inner loop
+    // around the pairs the convergence barrier would hold it until every lane of the warp had left that loop, i.e.
+    // until the warp's longest track ended.
     while (true) {
-        if (!alive) {
-            if (t >= P.n_tracks) break;
-            int2 s = __ldg(P.start + t);
-            row = s.x; col = s.y; k = 0; last = 4; hist = 4; hcount = 1; run_mask = 0x1EF;
-            if (P.traj != nullptr && P.traj_cap > 0) P.traj[t] = make_short2((short)row, (short)col);
-            if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
-            alive = true;
-        }
-        // Fast lane: pairs of ordinary steps (interior cell, previous move known, nu == 1, Philox stream, counts only,
-        // no trajectory store) run in a tight loop without the bookkeeping below; one Philox block feeds both steps
-        // of a pair, so there is no parity branch.  The loop carries the linear cell index only: a track whose
-        // distance to the nearest non-interior cell is m cannot leave the interior in m steps, so it takes
-        // floor((m + 1) / 2) pairs without looking at the border and then measures the distance again.  Anything
-        // else — first step, burn-in relocation or exit near the border, the move limit — leaves the loop and takes
-        // the general step.  Same arithmetic, same draws.
-        if (HAS_FIELDS && !EXACT && MEM1 && fast_lane && last != 4u && (k & 1) == 0) {
-            const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
-            const unsigned g0 = (unsigned)gid, g1 = (unsigned)(gid >> 32);
-            int lin = row * nc + col;
-            unsigned kp = (unsigned)k >> 1;
-            unsigned slot = slot_of(last);
-            int budget = 0;
-            float2 fc = make_float2(0.f, 0.f);
-            double uc = 0.0;
-            bool have_centre = false;
-            while (true) {
-                if (budget == 0) {
-                    row = lin / nc; col = lin - row * nc;
-                    const int m = min(min(row - 2, nr - 3 - row), min(col - 1, nc - 3 - col));
-                    budget = min((m + 1) >> 1, (kmax - (int)(2u * kp)) >> 1);
-                    if (budget <= 0) break;
-                    if (!have_centre) { fc = __ldg(P.fields + lin); uc = clip_updraft(fc.x); have_centre = true; }
+        if (budget == 0) {
+            if (in_fast) {                                                  // leave or refresh: canonical state back
+                const int lin = row;
+                row = lin / nc; col = lin - row * nc;
+                k *= 2;
+                last = flat_of(last);
+            } else if (!alive) {
+                if (t >= P.n_tracks) done = true;
+                else {
+                    int2 s = __ldg(P.start + t);
+                    row = s.x; col = s.y; k = 0; last = 4; hist = 4; hcount = 1; run_mask = 0x1EF;
+                    if (P.traj != nullptr && P.traj_cap > 0) P.traj[t] = make_short2((short)row, (short)col);
+                    if (P.presence != nullptr) atomicAdd(P.presence + (long long)row * nc + col, 1u);
+                    alive = true;
                 }
-                unsigned a, b, cc, dd;
-                philox4x32_10(g0, g1, kp, 0u, P, a, b, cc, dd);
-                fast_step(P, s_lut, nc, lin, slot, fc, uc, uniform52(a, b));
-                fast_step(P, s_lut, nc, lin, slot, fc, uc, uniform52(cc, dd));
-                ++kp; --budget;
             }
-            k = (int)(2u * kp);
-            last = flat_of(slot);
-        }
-        int r = row, c = col;
-        bool finish = k >= kmax;                                            // movmodel.py:285
-        if (!finish) {
-            if (k > P.burnin) {                                             // :287-289
-                finish = !(0 < r && r < nr - 1 && 0 < c && c < nc - 1);
-            } else {                                                        // :290-291, :205-217
-                if (r <= 1) r += 2; else if (r >= nr - 2) r -= 2;
-                if (c <= 0) c += 2; else if (c >= nc - 2) c -= 2;
+            if (!done) {
+                if (fast_lane && last != 4u && (k & 1) == 0) {
+                    const int m = min(min(row - 2, nr - 3 - row), min(col - 1, nc - 3 - col));
+                    budget = max(min((m + 1) >> 1, (kmax - k) >> 1), 0);
+                }
+                if (budget > 0) {
+                    row = row * nc + col;
+                    last = slot_of(last);
+                    k >>= 1;
+                    if (!in_fast) {
+                        fcen = __ldg(P.fields + row);
+                        ucen = clip_updraft(fcen.x);
+                        in_fast = true;
+                    }
+                } else {
+                    in_fast = false;
+                    // ---- one general step -------------------------------------------------------------------
+                    int r = row, c = col;
+                    bool finish = k >= kmax;                                    // movmodel.py:285
+                    if (!finish) {
+                        if (k > P.burnin) {                                     // :287-289
+                            finish = !(0 < r && r < nr - 1 && 0 < c && c < nc - 1);
+                        } else {                                                // :290-291, :205-217
+                            if (r <= 1) r += 2; else if (r >= nr - 2) r -= 2;
+                            if (c <= 0) c += 2; else if (c >= nc - 2) c -= 2;
+                        }
+                    }
+                    if (finish) {
+                        if (P.traj_len != nullptr) P.traj_len[t] = k + 1;
+                        steps_local += (unsigned long long)k;
+                        alive = false;
+                        // next track: first come, first served.  Track lengths are heavy-tailed (mean 1e4 steps, maximum
+                        // above 1e5), so a fixed list per thread would leave most lanes idle while a few work through
+                        // long lists; results do not depend on which lane steps which track (the random stream is keyed
+                        // by the track id, the counts are integer sums).
+                        t = stride + (long long)atomicAdd(P.next_track, 1ULL);
+                    } else {
+                        const int glin = r * nc + c;                            // rows * cols < 2^31 (checked on the host)
+                        const float2* base = HAS_FIELDS ? P.fields + glin : nullptr;
+                        const bool three = !EXACT && last != 4u && P.nu_is_one;
+                        // issue the gathers first so they overlap the random-number rounds
+                        int4 cand = make_int4(0, 0, 0, 0);
+                        float2 fc = make_float2(0.f, 0.f), f0 = fc, f1 = fc, f2 = fc;
+                        if (three) {
+                            cand = s_cand[last];
+                            if (HAS_FIELDS) {
+                                fc = __ldg(base);
+                                f0 = __ldg(base + cand.x);
+                                f1 = __ldg(base + cand.y);
+                                f2 = __ldg(base + cand.z);
+                            }
+                        }
+                        // direction-memory mask (:307-309)
+                        unsigned mask;
+                        if (MEM1) mask = (three ? 0u : restrict_mask(last));
+                        else if (P.memory == 0) mask = run_mask;
+                        else {
+                            mask = 0x1EF;
+                            int m = P.memory < hcount ? P.memory : hcount;
+                            for (int j = 0; j < m; ++j) mask &= restrict_mask((unsigned)((hist >> (4 * j)) & 15));
+                        }
+                        // one uniform per step (:312)
+                        double u;
+                        if (P.uniforms != nullptr) {
+                            u = __ldg(P.uniforms + t * P.ustride + k);
+                        } else {
+                            // Philox4x32-10 yields four words = two uniforms: counter (gid, k >> 1), words {0,1} for even k,
+                            // {2,3} for odd k
+                            if ((k & 1) == 0) {
+                                const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
+                                unsigned a, b;
+                                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, P, a, b, rng_c, rng_d);
+                                u = uniform52(a, b);
+                            } else {
+                                u = uniform52(rng_c, rng_d);
+                            }
+                        }
+                        int idx;
+                        if (EXACT) idx = choose_exact<HAS_FIELDS>(P, base, nc, mask, u);
+                        else if (three) {
+                            const int i0 = cand.w & 15, i1 = (cand.w >> 4) & 15, i2 = (cand.w >> 8) & 15;
+                            idx = choose_fast3<HAS_FIELDS, MEM1>(P, base, nc, mask, i0, i1, i2, fc, f0, f1, f2, u);
+                        } else idx = choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
+                        const int dr = ((idx * 11) >> 5) - 1;                   // idx / 3 - 1 for idx in 0..8
+                        const int dc = idx - 3 * (dr + 1) - 1;
+                        row = r + dr;                                           // :313-317
+                        col = c + dc;
+                        ++k;
+                        last = (unsigned)idx;
+                        if (!MEM1) {
+                            hist = (hist << 4) | (unsigned long long)idx;
+                            hcount = hcount < 16 ? hcount + 1 : 16;
+                            run_mask &= restrict_mask((unsigned)idx);
+                        }
+                        if (P.traj != nullptr && (long long)k < P.traj_cap)
+                            P.traj[(long long)k * P.n_tracks + t] = make_short2((short)row, (short)col);
+                        if (P.presence != nullptr) atomicAdd(P.presence + (glin + dr * nc + dc), 1u);
+                    }
+                }
             }
         }
-        if (finish) {
-            if (P.traj_len != nullptr) P.traj_len[t] = k + 1;
-            steps_local += (unsigned long long)k;
-            alive = false;
-            t += stride;
-            continue;
+        if (done) break;
+        if (budget > 0) {
+            const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
+            unsigned a, b, cc, dd;
+            philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)k, 0u, P, a, b, cc, dd);
+            fast_step(P, s_lut, nc, row, last, fcen, ucen, uniform52(a, b));
+            fast_step(P, s_lut, nc, row, last, fcen, ucen, uniform52(cc, dd));
+            ++k; --budget;
         }
-        const int lin = r * nc + c;                                         // rows * cols < 2^31 (checked on the host)
-        const float2* base = HAS_FIELDS ? P.fields + lin : nullptr;
-        const bool three = !EXACT && last != 4u && P.nu_is_one;
-        // issue the gathers first so they overlap the random-number rounds
-        int4 cand = make_int4(0, 0, 0, 0);
-        float2 fc = make_float2(0.f, 0.f), f0 = fc, f1 = fc, f2 = fc;
-        if (three) {
-            cand = s_cand[last];
-            if (HAS_FIELDS) {
-                fc = __ldg(base);
-                f0 = __ldg(base + cand.x);
-                f1 = __ldg(base + cand.y);
-                f2 = __ldg(base + cand.z);
-            }
-        }
-        // direction-memory mask (:307-309)
-        unsigned mask;
-        if (MEM1) mask = (three ? 0u : restrict_mask(last));
-        else if (P.memory == 0) mask = run_mask;
-        else {
-            mask = 0x1EF;
-            int m = P.memory < hcount ? P.memory : hcount;
-            for (int j = 0; j < m; ++j) mask &= restrict_mask((unsigned)((hist >> (4 * j)) & 15));
-        }
-        // one uniform per step (:312)
-        double u;
-        if (P.uniforms != nullptr) {
-            u = __ldg(P.uniforms + t * P.ustride + k);
-        } else {
-            // Philox4x32-10 yields four words = two uniforms: counter (gid, k >> 1), words {0,1} for even k, {2,3} for odd k
-            if ((k & 1) == 0) {
-                const unsigned long long gid = (unsigned long long)(P.track_id0 + t);
-                unsigned a, b;
-                philox4x32_10((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(k >> 1), 0u, P, a, b, rng_c, rng_d);
-                u = uniform52(a, b);
-            } else {
-                u = uniform52(rng_c, rng_d);
-            }
-        }
-        int idx;
-        if (EXACT) idx = choose_exact<HAS_FIELDS>(P, base, nc, mask, u);
-        else if (three) {
-            const int i0 = cand.w & 15, i1 = (cand.w >> 4) & 15, i2 = (cand.w >> 8) & 15;
-            idx = choose_fast3<HAS_FIELDS, MEM1>(P, base, nc, mask, i0, i1, i2, fc, f0, f1, f2, u);
-        } else idx = choose_fast_general<HAS_FIELDS>(P, base, nc, mask, u);
-        const int dr = ((idx * 11) >> 5) - 1;                               // idx / 3 - 1 for idx in 0..8
-        const int dc = idx - 3 * (dr + 1) - 1;
-        row = r + dr;                                                       // :313-317
-        col = c + dc;
-        ++k;
-        last = (unsigned)idx;
-        if (!MEM1) {
-            hist = (hist << 4) | (unsigned long long)idx;
-            hcount = hcount < 16 ? hcount + 1 : 16;
-            run_mask &= restrict_mask((unsigned)idx);
-        }
-        if (P.traj != nullptr && (long long)k < P.traj_cap)
-            P.traj[(long long)k * P.n_tracks + t] = make_short2((short)row, (short)col);
-        if (P.presence != nullptr) atomicAdd(P.presence + (lin + dr * nc + dc), 1u);
     }
     if (P.total_steps != nullptr) {
         // one atomic per warp
@@ -521,6 +573,26 @@ __global__ void presence_from_traj_kernel(const short2* __restrict__ traj, long 
 }  // namespace ssrs
 
 using namespace ssrs;
+
+namespace {
+// Track-queue counters: one 8-byte slot per launch, taken round-robin from a small per-device array and zeroed on the
+// launch's stream.  A slot is reused 1024 launches later, long after its launch has drained.
+constexpr int kQueueSlots = 1024;
+constexpr int kMaxDevices = 64;
+unsigned long long* g_queue[kMaxDevices] = {nullptr};
+unsigned g_queue_next[kMaxDevices] = {0};
+std::mutex g_queue_mutex;
+
+int queue_slot(unsigned long long** slot) {
+    int dev = 0;
+    SSRS_CUDA_TRY(cudaGetDevice(&dev));
+    SSRS_REQUIRE(dev >= 0 && dev < kMaxDevices, "ssrs_step_tracks: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_queue_mutex);
+    if (g_queue[dev] == nullptr) SSRS_CUDA_TRY(cudaMalloc(&g_queue[dev], kQueueSlots * sizeof(unsigned long long)));
+    *slot = g_queue[dev] + (g_queue_next[dev]++ % kQueueSlots);
+    return SSRS_OK;
+}
+}  // namespace
 
 extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const int32_t* start_rc, int64_t n_tracks,
                                 int64_t track_id0, const double* dirprob9_host, int memory, double nu, uint64_t seed,
@@ -584,6 +656,11 @@ extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const i
     long long blocks = cdiv(n_tracks, threads);
     const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
+    {
+        const int rc = queue_slot(&P.next_track);
+        if (rc != SSRS_OK) return rc;
+    }
+    SSRS_CUDA_TRY(cudaMemsetAsync(P.next_track, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
     kern<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(P);
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
