@@ -1,10 +1,10 @@
-"""Times the stepping kernel on the bench grid for several settings of the tail-prefetch / presence-hint knobs
-(SSRS_STEP_PF_K, SSRS_STEP_PF_MINK, SSRS_STEP_RED_HINT) and track counts; checks that the presence raster is identical."""
+"""Times the stepping kernel on the bench grid for several settings of SSRS_STEP_TAIL_LANES (tail-mode L1 prefetch) and
+track counts; checks that the presence raster is identical for every setting."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import argparse
-ap = argparse.ArgumentParser(); ap.add_argument("--tracks", type=int, nargs="+", default=[1024, 100_000, 1_000_000])
-ap.add_argument("--cfg", type=str, nargs="+", default=["0,0,0", "4,0,0", "8,0,0", "16,0,0", "32,0,0", "8,15000,0", "16,15000,0", "0,0,1", "8,0,1", "16,15000,1"])
+ap = argparse.ArgumentParser(); ap.add_argument("--tracks", type=int, nargs="+", default=[32, 1024, 100_000, 1_000_000])
+ap.add_argument("--lanes", type=int, nargs="+", default=[0, 1, 2, 4, 8, 16, 32])
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 import bench
@@ -17,9 +17,8 @@ for n in a.tracks:
     A.tracks_per_gpu = n
     sr, sc = bench.start_cells(A, n)
     ref = None
-    for cfg in a.cfg:
-        pfk, mink, hint = cfg.split(",")
-        os.environ["SSRS_STEP_PF_K"] = pfk; os.environ["SSRS_STEP_PF_MINK"] = mink; os.environ["SSRS_STEP_RED_HINT"] = hint
+    for lanes in a.lanes:
+        os.environ["SSRS_STEP_TAIL_LANES"] = str(lanes)
         best = 1e30
         for rep in range(a.reps):
             presence = torch.zeros(shape, dtype=torch.int32, device="cuda"); total = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -30,4 +29,4 @@ for n in a.tracks:
             best = min(best, e0.elapsed_time(e1))
         if ref is None: ref = presence.clone()
         same = bool((presence == ref).all().item())
-        print(f"tracks {n} pf_k {pfk} mink {mink} hint {hint}: {best:.2f} ms, {int(total.item()) / best / 1e6:.2f} G track-steps/s, identical {same}", flush=True)
+        print(f"tracks {n} tail_lanes {lanes}: {best:.2f} ms, {int(total.item()) / best / 1e6:.2f} G track-steps/s, identical {same}", flush=True)
