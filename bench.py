@@ -34,9 +34,9 @@ UNIT = "track-steps/s"
 STEP_BYTES = 76          # 72 B of 3x3 gathers on two f32 fields + 4 B presence atomic (no trajectory store)
 STENCIL_BYTES = 20       # 4 B DEM + 4 outputs x 4 B
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_tracks_kernel launch of the default workload, from the
-# `ncu --set full` capture of this command (profiles/r01_ncu_step_tracks_fastlane.txt): 637.2 MB + 155.2 MB.  Far below
-# the 76.6 GB of algorithmic gather bytes: the gathers are served by L1 (52 % hits) and L2 (86 % hits).
-STEP_TRAFFIC_DEFAULT = 792.4e6
+# `ncu --set full` capture of this command (profiles/r01_ncu_step_tracks_v8.txt): 621.6 MB + 160.7 MB.  Far below
+# the 78.5 GB of algorithmic gather bytes: the gathers are served by L1 (43 % hits) and L2 (81 % hits).
+STEP_TRAFFIC_DEFAULT = 782.2e6
 
 
 def parse():
@@ -316,7 +316,7 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "peak_source": peak_src,
                          "bytes_per_track_step": STEP_BYTES, "kernel_ms": kernel_ms,
-                         "note": "not HBM-bound by construction (SURVEY §8d): gathers hit L1/L2 (ncu: L2 hit 86 %, DRAM throughput 0.2 %); "
+                         "note": "not HBM-bound by construction (SURVEY §8d): gathers hit L1/L2 (ncu: L2 hit 81 %, DRAM throughput 0.2 %); "
                                  "the launch lasts as long as its longest track (instruction-latency bound tail); "
                                  "HBM fraction reported as the contract asks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
