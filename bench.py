@@ -26,8 +26,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL writes its version banner / debug lines to stdout by default; stdout carries exactly one JSON line
+# stdout carries exactly one JSON line.  NCCL (and anything else below Python) may write banners straight to file
+# descriptor 1 — NCCL_DEBUG_FILE does not cover its version line — so descriptor 1 is pointed at stderr for the whole run
+# and the JSON line goes through a private duplicate of the original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "track-steps/sec"
 UNIT = "track-steps/s"
@@ -334,7 +344,7 @@ def main():
                                 "sample": f"{n_sample} of the same tracks on the same fields, {nsteps} track-steps in {dt:.1f} s "
                                           f"(oracle/ssrs_oracle.c, OpenMP); the reference's own Python stepper runs "
                                           f"~1e4 track-steps/s/core (BASELINE.md)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         D.destroy_native_comm()
@@ -391,7 +401,7 @@ def reference_arm(a):
                              "sample": f"{n_sample} tracks per step ({steps_done // a.steps} track-steps), "
                                        f"oracle/ssrs_oracle.c with OpenMP on {threads} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
