@@ -251,6 +251,7 @@ struct Level {
     i64* rowptr = nullptr; int* col = nullptr; double* val = nullptr;       // CSR (levels >= 1)
     int* agg = nullptr; i64 nc = 0; i64* memptr = nullptr; int* mem = nullptr;  // map to the next level
     i64* sptr = nullptr; int* ecol = nullptr; float* eval = nullptr; i64 ell_entries = 0;   // sliced ELL, float32 (levels >= 1)
+    unsigned* epack = nullptr;     // packed entries (bf16 value | 16-bit column offset) when every offset fits; then ecol/eval are unused
     float *excess = nullptr, *dinv = nullptr;                                 // per-row operator data, float32 like the entries
     real *x32 = nullptr, *b32 = nullptr, *t32 = nullptr, *r32 = nullptr;      // cycle vectors (levels >= 1)
     // row-sharded solve: ownership of this level's nodes and, per part, the index range its rows reference
@@ -562,12 +563,32 @@ struct Ell {
     const i64* sptr;        // [slices + 1]
     const int* col;
     const float* val;
+    const unsigned* pack;   // packed entries, or nullptr: then col/val hold the entries
     const float* excess;   // a_ii + sum_off a_ij (formed in float64, rounded once)
     const float* dinv;     // 1 / a_ii
     i64 n;
 };
-template <class X>
-SSRS_HD inline real ell_apply(const Ell& e, i64 i, const X& x) {
+// Packed entry: high half = the value rounded to bfloat16 (the upper 16 bits of its float32), low half = column - row
+// as a signed 16-bit offset.  Half the bytes of {int32 column, float32 value}; the sweeps over the coarse levels are
+// bound by exactly these bytes.  The 8 significant bits only perturb the off-diagonal weights of a preconditioner:
+// the row's anchoring (`excess`, formed from the exact sums) and the diagonal stay float32, and the difference form
+// keeps the constant mode exact whatever the weights are.
+SSRS_HD inline unsigned pack_entry(float v, i64 delta) {
+    unsigned u;
+    memcpy(&u, &v, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);                       // round to nearest even at bit 16
+    return (u & 0xFFFF0000u) | ((unsigned)(int)delta & 0xFFFFu);
+}
+SSRS_HD inline float packed_value(unsigned w) {
+    const unsigned u = w & 0xFFFF0000u;
+    float v;
+    memcpy(&v, &u, 4);
+    return v;
+}
+SSRS_HD inline i64 packed_col(unsigned w, i64 i) { return i + (i64)(short)(w & 0xFFFFu); }
+
+template <bool PACKED, class X>
+SSRS_HD inline real ell_apply_fmt(const Ell& e, i64 i, const X& x) {
     const i64 s = i >> 5;
     const i64 p1 = e.sptr[s + 1];
     const real xi = x(i);
@@ -576,13 +597,28 @@ SSRS_HD inline real ell_apply(const Ell& e, i64 i, const X& x) {
     // four entries per trip: the column indices, then the gathers they address, are independent loads — a row's
     // entries are otherwise a chain of dependent L2 round trips (the small levels are pure latency)
     for (; p + 96 < p1; p += 128) {
-        const int c0 = e.col[p], c1 = e.col[p + 32], c2 = e.col[p + 64], c3 = e.col[p + 96];
-        const float v0 = e.val[p], v1 = e.val[p + 32], v2 = e.val[p + 64], v3 = e.val[p + 96];
+        i64 c0, c1, c2, c3;
+        float v0, v1, v2, v3;
+        if (PACKED) {
+            const unsigned w0 = e.pack[p], w1 = e.pack[p + 32], w2 = e.pack[p + 64], w3 = e.pack[p + 96];
+            c0 = packed_col(w0, i); c1 = packed_col(w1, i); c2 = packed_col(w2, i); c3 = packed_col(w3, i);
+            v0 = packed_value(w0); v1 = packed_value(w1); v2 = packed_value(w2); v3 = packed_value(w3);
+        } else {
+            c0 = e.col[p]; c1 = e.col[p + 32]; c2 = e.col[p + 64]; c3 = e.col[p + 96];
+            v0 = e.val[p]; v1 = e.val[p + 32]; v2 = e.val[p + 64]; v3 = e.val[p + 96];
+        }
         const real x0 = x(c0), x1 = x(c1), x2 = x(c2), x3 = x(c3);
         acc += (v0 * (x0 - xi) + v1 * (x1 - xi)) + (v2 * (x2 - xi) + v3 * (x3 - xi));
     }
-    for (; p < p1; p += 32) acc += e.val[p] * (x(e.col[p]) - xi);
+    for (; p < p1; p += 32) {
+        if (PACKED) { const unsigned w = e.pack[p]; acc += packed_value(w) * (x(packed_col(w, i)) - xi); }
+        else acc += e.val[p] * (x(e.col[p]) - xi);
+    }
     return e.excess[i] * xi + acc;
+}
+template <class X>
+SSRS_HD inline real ell_apply(const Ell& e, i64 i, const X& x) {
+    return e.pack != nullptr ? ell_apply_fmt<true>(e, i, x) : ell_apply_fmt<false>(e, i, x);
 }
 inline int ell_first32(const Ell e, i64 i0, i64 i1, const real* b, real* x, real omega, stream_t st) {
     return pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { x[i] = omega * e.dinv[i] * b[i]; });
@@ -604,6 +640,7 @@ inline int ell_jacobi32(const Ell e, i64 i0, i64 i1, const real* b, const real* 
 // of the CSR arrays instead of a thread walking an ELL row: same operator (float32-rounded entries, difference form),
 // a handful of coalesced trips instead of a chain of dependent gathers.
 constexpr i64 SMALL_ROWS = 32768;
+static bool g_ell_packed = true;     // SSRS_X_ELLPACK=0 keeps {int32, float32} entries (A/B measurements)
 SSRS_HD inline real csr_row_partial(const CsrGraph& g, i64 i, int lane, const real* x) {
     const real xi = x[i];
     real acc = (real)0.0;
@@ -660,7 +697,7 @@ struct Hierarchy {
 };
 
 inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; g.parts = L.parts; return g; }
-inline Ell ell_of(const Level& L) { Ell e; e.sptr = L.sptr; e.col = L.ecol; e.val = L.eval; e.excess = L.excess; e.dinv = L.dinv; e.n = L.n; return e; }
+inline Ell ell_of(const Level& L) { Ell e; e.sptr = L.sptr; e.col = L.ecol; e.val = L.eval; e.pack = L.epack; e.excess = L.excess; e.dinv = L.dinv; e.n = L.n; return e; }
 
 inline int level_residual(const Level& L, i64 i0, i64 i1, const real* b, const real* x, real* res, stream_t st) {
     if (L.n <= SMALL_ROWS) return csr_residual32(csr_of(L), L.excess, i0, i1, b, x, res, st);
@@ -725,10 +762,19 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
     }));
     i64 total = 0;
     AMG_TRY(exclusive_scan_i64(sptr, slices + 1, &total, st));
-    AMG_ALLOC(L.ecol, int, total);
-    AMG_ALLOC(L.eval, float, total);
+    // packed 4-byte entries when every column lies within +-32767 of its row (node numbering follows the raster, so
+    // this holds unless a raster row has more than ~1e5 cells); else {int32 column, float32 value}
+    double far_entries = 0.0;
+    AMG_TRY(preduce_sum(n, st, &far_entries, [=] SSRS_HD(i64 i) {
+        double cnt = 0.0;
+        for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) { const i64 dlt = (i64)g.col[k] - i; cnt += (dlt > 32767 || dlt < -32767) ? 1.0 : 0.0; }
+        return cnt;
+    }));
+    const bool packed = g_ell_packed && far_entries == 0.0;
     L.ell_entries = total;
-    int* ecol = L.ecol; float* eval = L.eval;
+    if (packed) { AMG_ALLOC(L.epack, unsigned, total); }
+    else { AMG_ALLOC(L.ecol, int, total); AMG_ALLOC(L.eval, float, total); }
+    int* ecol = L.ecol; float* eval = L.eval; unsigned* epack = L.epack;
     AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
         const i64 s = i >> 5;
         i64 p = sptr[s] + (i & 31);
@@ -737,10 +783,14 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
         for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) {
             if (g.col[k] == (int)i) { d = g.val[k]; continue; }
             off += g.val[k];
-            ecol[p] = g.col[k]; eval[p] = (float)g.val[k];
+            if (packed) epack[p] = pack_entry((float)g.val[k], (i64)g.col[k] - i);
+            else { ecol[p] = g.col[k]; eval[p] = (float)g.val[k]; }
             p += 32;
         }
-        for (; p < p1; p += 32) { ecol[p] = (int)i; eval[p] = 0.0f; }
+        for (; p < p1; p += 32) {
+            if (packed) epack[p] = 0u;
+            else { ecol[p] = (int)i; eval[p] = 0.0f; }
+        }
         excess[i] = (float)(d + off);
         dinv[i] = (float)(1.0 / d);
     }));
@@ -988,6 +1038,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
 #endif
     Pool pool(st);
     Hierarchy H;
+    g_ell_packed = !(getenv("SSRS_X_ELLPACK") && atoi(getenv("SSRS_X_ELLPACK")) == 0);
     if (getenv("SSRS_X_OC")) H.overcorrect = (float)atof(getenv("SSRS_X_OC"));
     if (getenv("SSRS_X_OMEGA")) H.omega = (float)atof(getenv("SSRS_X_OMEGA"));
     if (getenv("SSRS_X_NU")) H.nu = atoi(getenv("SSRS_X_NU"));
