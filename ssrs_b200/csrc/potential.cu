@@ -470,8 +470,31 @@ int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
 // difference form, (A x)_i = excess_i x_i + sum_j a_ij (x_j - x_i), with the row excess (the anchoring to the
 // Dirichlet set) formed in float64.  The outer BiCGStab iteration evaluates the exact float64 operator, so
 // rounding inside the cycle cannot change the solution it converges to.
+// bfloat16 pairs in one word: .lo() = low half, .hi() = high half, each the upper 16 bits of a float32
+struct Bf16Pairs {
+    const unsigned* p;
+    SSRS_HD float lo(i64 i) const { const unsigned u = p[i] << 16; float v; memcpy(&v, &u, 4); return v; }
+    SSRS_HD float hi(i64 i) const { const unsigned u = p[i] & 0xFFFF0000u; float v; memcpy(&v, &u, 4); return v; }
+};
+SSRS_HD inline unsigned bf16_bits(float v) {               // round to nearest even
+    unsigned u;
+    memcpy(&u, &v, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return u >> 16;
+}
+// Forward link weights of the cycle's fine-level operator, 0 where the neighbour is outside the grid, as bfloat16
+// pairs {E, N} and {NE, NW}: 8 bytes per cell instead of 16 in passes that are bound by their bytes, and six weight
+// loads per cell instead of eight.  Like the coarse levels' packed entries this only perturbs a preconditioner (the
+// difference form keeps the constant mode exact; the diagonal `dinv` is formed from the float32 weights).
+struct Fine32W {
+    Bf16Pairs en, dd;
+    SSRS_HD float E(i64 i) const { return en.lo(i); }
+    SSRS_HD float N(i64 i) const { return en.hi(i); }
+    SSRS_HD float NE(i64 i) const { return dd.lo(i); }
+    SSRS_HD float NW(i64 i) const { return dd.hi(i); }
+};
 struct Fine32 {
-    const float *wE, *wN, *wNE, *wNW;   // forward link weights, 0 where the neighbour is outside the grid
+    Fine32W w;
     const float* dinv;                 // 1 / (sum of the eight link weights); 0 at Dirichlet nodes
     const float* kd;                    // conductivity, sign bit = Dirichlet
     int rows, cols;
@@ -485,10 +508,11 @@ SSRS_HD inline real fine_apply32(const Fine32& F, int r, int c, const X& x) {
     if (r > 0 && r < F.rows - 1 && c > 0 && c < cols - 1) {
         // interior cell (all but the raster's border; the quirk column is on the border): fixed offsets, same order
         const real xi = x(i);
-        real s = F.wE[i] * (xi - x(i + 1)) + F.wE[i - 1] * (xi - x(i - 1));
-        s += F.wN[i] * (xi - x(i + cols)) + F.wN[i - cols] * (xi - x(i - cols));
-        s += F.wNE[i] * (xi - x(i + cols + 1)) + F.wNE[i - cols - 1] * (xi - x(i - cols - 1));
-        s += F.wNW[i] * (xi - x(i + cols - 1)) + F.wNW[i - cols + 1] * (xi - x(i - cols + 1));
+        const Fine32W& w = F.w;
+        real s = w.E(i) * (xi - x(i + 1)) + w.E(i - 1) * (xi - x(i - 1));
+        s += w.N(i) * (xi - x(i + cols)) + w.N(i - cols) * (xi - x(i - cols));
+        s += w.NE(i) * (xi - x(i + cols + 1)) + w.NE(i - cols - 1) * (xi - x(i - cols - 1));
+        s += w.NW(i) * (xi - x(i + cols - 1)) + w.NW(i - cols + 1) * (xi - x(i - cols + 1));
         return s;
     }
     const bool hW = c > 0, hE = c < cols - 1, hS = r > 0, hN = r < F.rows - 1;
@@ -496,16 +520,17 @@ SSRS_HD inline real fine_apply32(const Fine32& F, int r, int c, const X& x) {
     const i64 jE = hE ? i + 1 : i, jW = hW ? i - 1 : i, jN = hN ? i + cols : i, jS = hS ? i - cols : i;
     const i64 jNE = (hN && hE) ? i + cols + 1 : i, jNW = (hN && hW) ? i + cols - 1 : i;
     const i64 jSW = (hS && hW) ? i - cols - 1 : i, jSE = (hS && hE) ? i - cols + 1 : i;
-    real wS = F.wN[jS], wSW = F.wNE[jSW];
+    const Fine32W& w = F.w;
+    real wS = w.N(jS), wSW = w.NE(jSW);
     if (c == cols - 1 && hS && hN) {                                        // movmodel.py:73-79
         wS = (real)link_weight<false>(F.kd[i], F.kd[jS], true);
         wSW = (real)link_weight<false>(F.kd[i], F.kd[jSW], false);
     }
     const real xi = x(i);
-    real s = F.wE[i] * (xi - x(jE)) + F.wE[jW] * (xi - x(jW));
-    s += F.wN[i] * (xi - x(jN)) + wS * (xi - x(jS));
-    s += F.wNE[i] * (xi - x(jNE)) + wSW * (xi - x(jSW));
-    s += F.wNW[i] * (xi - x(jNW)) + F.wNW[jSE] * (xi - x(jSE));
+    real s = w.E(i) * (xi - x(jE)) + w.E(jW) * (xi - x(jW));
+    s += w.N(i) * (xi - x(jN)) + wS * (xi - x(jS));
+    s += w.NE(i) * (xi - x(jNE)) + wSW * (xi - x(jSW));
+    s += w.NW(i) * (xi - x(jNW)) + w.NW(jSE) * (xi - x(jSE));
     return s;
 }
 
@@ -1098,8 +1123,12 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         }
     }
     {
-        float *wf, *dinv; double* wd;
-        AMG_ALLOC(wf, float, 4 * n);
+        float *wf, *dinv; double* wd; unsigned *wen, *wdd;
+        Pool wtmp(st, true);                                   // float32 weights: only needed to form the diagonal
+        wf = wtmp.get<float>(4 * n);
+        if (!wf) { set_error("ssrs_potential_solve: out of device memory (fine weights)"); return SSRS_ERR_CUDA; }
+        AMG_ALLOC(wen, unsigned, n);
+        AMG_ALLOC(wdd, unsigned, n);
         AMG_ALLOC(wd, double, 4 * n);
         AMG_ALLOC(dinv, float, n);
         const FineGraph fgw = H.fine;
@@ -1113,21 +1142,24 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             const double nw = (hasN && hasW) ? link_weight<false>(kc, fgw.kd[i + cols - 1], true) : 0.0;
             wd[i] = e; wd[n + i] = nn; wd[2 * n + i] = ne; wd[3 * n + i] = nw;
             wf[i] = (float)e; wf[n + i] = (float)nn; wf[2 * n + i] = (float)ne; wf[3 * n + i] = (float)nw;
+            wen[i] = bf16_bits((float)e) | (bf16_bits((float)nn) << 16);
+            wdd[i] = bf16_bits((float)ne) | (bf16_bits((float)nw) << 16);
         }));
-        H.fw.wf = wf; H.fw.wd = wd;
+        H.fw.wf = nullptr; H.fw.wd = wd;
         Fine32 F;
-        F.wE = wf; F.wN = wf + n; F.wNE = wf + 2 * n; F.wNW = wf + 3 * n; F.dinv = dinv; F.kd = kd; F.rows = rows; F.cols = cols;
+        F.w.en.p = wen; F.w.dd.p = wdd; F.dinv = dinv; F.kd = kd; F.rows = rows; F.cols = cols;
+        const float *fE = wf, *fN = wf + n, *fNE = wf + 2 * n, *fNW = wf + 3 * n;
         AMG_TRY(pfor2d(rows, cols, st, [=] SSRS_HD(int r, int c) {       // Jacobi diagonal of the float32 operator
             const i64 i = (i64)r * cols + c;
             if (fgw.excluded(i)) { dinv[i] = 0.0f; return; }
             const bool hW = c > 0, hE = c < cols - 1, hS = r > 0, hN = r < rows - 1;
-            real wS = hS ? F.wN[i - cols] : (real)0.0, wSW = (hS && hW) ? F.wNE[i - cols - 1] : (real)0.0;
+            real wS = hS ? fN[i - cols] : (real)0.0, wSW = (hS && hW) ? fNE[i - cols - 1] : (real)0.0;
             if (c == cols - 1 && hS && hN) {
                 wS = (real)link_weight<false>(F.kd[i], F.kd[i - cols], true);
                 wSW = (real)link_weight<false>(F.kd[i], F.kd[i - cols - 1], false);
             }
-            const real d = ((F.wE[i] + (hW ? F.wE[i - 1] : (real)0.0)) + (F.wN[i] + wS)) +
-                            ((F.wNE[i] + wSW) + (F.wNW[i] + ((hS && hE) ? F.wNW[i - cols + 1] : (real)0.0)));
+            const real d = ((fE[i] + (hW ? fE[i - 1] : (real)0.0)) + (fN[i] + wS)) +
+                            ((fNE[i] + wSW) + (fNW[i] + ((hS && hE) ? fNW[i - cols + 1] : (real)0.0)));
             dinv[i] = (float)((real)1.0 / d);
         }));
         H.f32 = F;
