@@ -213,6 +213,13 @@ SSRS_API int ssrs_interp_wind(const double* px, const double* py, const double* 
                               const int32_t* triangles, int ntriangles, double x0, double y0, double resolution,
                               int rows, int cols, int32_t* owner_scratch, float* wspeed, float* wdirn, void* stream);
 
+/* The same for Config.wtk_interp_type = 'nearest' (ssrs/config.py:60; scipy griddata(method='nearest'), a k-d tree
+ * query): every cell takes the u/v of its closest site (float64 Euclidean distance; equal distances go to the lower
+ * site index), defined everywhere — no triangulation, no NaN. */
+SSRS_API int ssrs_interp_wind_nearest(const double* px, const double* py, const double* east, const double* north,
+                                      int npoints, double x0, double y0, double resolution, int rows, int cols,
+                                      float* wspeed, float* wdirn, void* stream);
+
 /* compute_thermals (ssrs/layers.py:188-214) in two steps: the random seeds (Philox4x32-10 keyed by (seed, cell):
  * same distribution as the reference's np.random draws, not the same stream) and the deterministic
  * scipy.ndimage.gaussian_filter(sigma, mode='constant', truncate) smoothing.  tmp: float32 [rows][cols];

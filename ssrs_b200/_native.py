@@ -25,6 +25,8 @@ EXPORTS = {
                                                C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_interp_wind": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_interp_wind_nearest": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_thermal_seeds": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ssrs_gaussian_blur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                      C.c_void_p, C.c_void_p]),

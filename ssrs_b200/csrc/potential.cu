@@ -12,7 +12,7 @@
 //     on the 1e-8 floor), so coarsening must follow the strong couplings: per level one pass of pairwise
 //     matching by mutual strongest connection (handshake rounds), then unmatched nodes join the aggregate
 //     of their strongest neighbour.  Prolongation is piecewise constant, coarse operators are Galerkin
-//     sums (CSR for setup, float32 sliced ELL for the cycle), smoothing is weighted Jacobi, V(1,1) cycle with an
+//     sums (CSR for setup, sliced ELL with 4-byte bfloat16 entries for the cycle), smoothing is weighted Jacobi, V(1,1) cycle with an
 //     over-corrected coarse-grid correction, dense float64 inverse on the coarsest level;
 //   * outer iteration: right-preconditioned BiCGStab in float64 (the last-column quirk makes the operator
 //     non-symmetric), true-residual restarts; result rounded to float32 like the reference (:128).
@@ -461,8 +461,9 @@ int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
 }
 
 // ---- the cycle: float32 operators, float64 vectors ------------------------------------------------------
-// The V-cycle is only a preconditioner, so its operators are stored in float32 (fine level: 4 forward link
-// weights per cell; coarse levels: sliced ELL), computed in float64 and rounded once.  Its VECTORS stay float64:
+// The V-cycle is only a preconditioner, so its operators are stored in reduced precision (fine level: 4 forward link
+// weights per cell as bfloat16 pairs; coarse levels: sliced ELL with bfloat16 values; diagonals and row anchoring in
+// float32), computed in float64 and rounded once.  Its VECTORS stay float64:
 // with conductances spanning 1e-8..1 a conducting island is anchored to the rest of the grid by links 1e-8 of
 // its internal ones, so float32 rounding noise of an island's (large, nearly constant) correction, multiplied by
 // the strong internal links in the outer A*y, swamps the signal carried by the weak links — a float32-vector

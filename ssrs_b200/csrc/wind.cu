@@ -101,6 +101,76 @@ __global__ void __launch_bounds__(256) interp_wind_kernel(const double* __restri
     wdirn[i] = d;
 }
 
+// ---- nearest-site interpolation (wtk_interp_type = 'nearest') -------------------------------------------
+// scipy's griddata(method='nearest') is a k-d tree query: the value of the closest site in Euclidean distance,
+// defined everywhere (no hull).  A CTA owns 32 x 8 cells.  With c the CTA's centre, R the largest distance from c to
+// one of its cell centres and d_min the distance from c to its closest site, the closest site of ANY cell of the CTA
+// lies within d_min + 2R of c (triangle inequality), so the CTA first filters the sites by that bound (a handful
+// survive for sites a few hundred cells apart) and each cell then tests only the survivors, in float64 like the tree
+// and with separately rounded products so that ties resolve identically; equal distances go to the lower site index.
+constexpr int NEAREST_MAX_CAND = 256;
+
+__device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
+    const double dx = ax - bx, dy = ay - by;
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+__global__ void __launch_bounds__(256) nearest_wind_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                                           const double* __restrict__ east, const double* __restrict__ north,
+                                                           int npoints, double x0, double y0, double res, int rows, int cols,
+                                                           float* __restrict__ wspeed, float* __restrict__ wdirn) {
+    __shared__ double s_red[8];
+    __shared__ double s_bound2;
+    __shared__ int s_cnt;
+    __shared__ int s_cand[NEAREST_MAX_CAND];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const double cx = x0 + (blockIdx.x * 32 + 15.5) * res, cy = y0 + (blockIdx.y * 8 + 3.5) * res;
+    double m = 1.0e300;
+    for (int j = tid; j < npoints; j += 256) m = fmin(m, dist2(cx, cy, px[j], py[j]));
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = m;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double mm = s_red[0];
+        for (int w = 1; w < 8; ++w) mm = fmin(mm, s_red[w]);
+        const double R = res * 15.890248582070704;                    // sqrt(15.5^2 + 3.5^2) cells
+        const double b = (sqrt(mm) + 2.0 * R) * (1.0 + 1e-12);
+        s_bound2 = b * b;
+    }
+    __syncthreads();
+    const double bound2 = s_bound2;
+    for (int j = tid; j < npoints; j += 256)
+        if (dist2(cx, cy, px[j], py[j]) <= bound2) {
+            const int k = atomicAdd(&s_cnt, 1);
+            if (k < NEAREST_MAX_CAND) s_cand[k] = j;
+        }
+    __syncthreads();
+    const int cnt = s_cnt;
+    const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+    if (r >= rows || c >= cols) return;
+    const double x = x0 + c * res, y = y0 + r * res;
+    double best = 1.0e300;
+    int bj = 0x7fffffff;
+    if (cnt <= NEAREST_MAX_CAND) {
+        for (int k = 0; k < cnt; ++k) {
+            const int j = s_cand[k];
+            const double d = dist2(x, y, px[j], py[j]);
+            if (d < best || (d == best && j < bj)) { best = d; bj = j; }
+        }
+    } else {                                                          // too many survivors (very dense sites): scan all
+        for (int j = 0; j < npoints; ++j) {
+            const double d = dist2(x, y, px[j], py[j]);
+            if (d < best) { best = d; bj = j; }
+        }
+    }
+    const double e = east[bj], n = north[bj];
+    const double two_pi = 6.283185307179586;
+    const long long i = (long long)r * cols + c;
+    wspeed[i] = (float)sqrt(e * e + n * n);                                              // simulator.py:787-788
+    wdirn[i] = (float)(fmod(atan2(e, n) + two_pi, two_pi) * (180.0 / 3.141592653589793));   // :789-791
+}
+
 // ---- thermals -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
                                               unsigned& o0, unsigned& o1, unsigned& o2, unsigned& o3) {
@@ -179,6 +249,18 @@ extern "C" int ssrs_interp_wind(const double* px, const double* py, const double
     dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 8));
     interp_wind_kernel<<<grid, dim3(32, 8), 0, st>>>(px, py, east, north, triangles, x0, y0, resolution, rows, cols,
                                                      owner_scratch, wspeed, wdirn);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int ssrs_interp_wind_nearest(const double* px, const double* py, const double* east, const double* north, int npoints,
+                                        double x0, double y0, double resolution, int rows, int cols, float* wspeed,
+                                        float* wdirn, void* stream) {
+    SSRS_REQUIRE(px && py && east && north && wspeed && wdirn, "ssrs_interp_wind_nearest: NULL buffer");
+    SSRS_REQUIRE(npoints >= 1 && rows > 0 && cols > 0 && resolution > 0.0, "ssrs_interp_wind_nearest: bad sizes");
+    dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 8));
+    nearest_wind_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(px, py, east, north, npoints, x0, y0,
+                                                                                 resolution, rows, cols, wspeed, wdirn);
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
 }

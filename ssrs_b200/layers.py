@@ -138,10 +138,12 @@ def delaunay_triangles(xlocs, ylocs):
 def interpolate_wind_to_grid(xlocs, ylocs, wspeed, wdirn, x0: float, y0: float, res: float, gridsize,
                              triangles=None, method: str = 'linear'):
     """Reference `Simulator._get_interpolated_wind_conditions` (`simulator.py:778-792`): wind speed/direction at
-    scattered sites -> CUDA float32 rasters `[rows, cols]` (speed, direction in degrees), NaN outside the sites'
-    convex hull.  `triangles` may be passed to reuse one triangulation for many wind cases."""
-    if method != 'linear':
-        raise NotImplementedError(f"wtk_interp_type={method!r}: only 'linear' (the Config default) runs on the GPU")
+    scattered sites -> CUDA float32 rasters `[rows, cols]` (speed, direction in degrees).  `method` is
+    `Config.wtk_interp_type`: 'linear' (the default; NaN outside the sites' convex hull; `triangles` may be passed to
+    reuse one triangulation for many wind cases) or 'nearest' (closest site, defined everywhere).  scipy's 'cubic'
+    (Clough-Tocher) is not built."""
+    if method not in ('linear', 'nearest'):
+        raise NotImplementedError(f"wtk_interp_type={method!r}: 'linear' (the Config default) and 'nearest' run on the GPU")
     torch = N.require_cuda()
     lib = N.load()
     x = np.ascontiguousarray(xlocs, dtype=np.float64)
@@ -152,6 +154,16 @@ def interpolate_wind_to_grid(xlocs, ylocs, wspeed, wdirn, x0: float, y0: float, 
         raise ValueError("site coordinates and wind values must be 1-D arrays of equal length (>= 3 sites)")
     east = np.multiply(ws, np.sin(wd * np.pi / 180.))               # simulator.py:784-785
     north = np.multiply(ws, np.cos(wd * np.pi / 180.))
+    if method == 'nearest':
+        rows, cols = int(gridsize[0]), int(gridsize[1])
+        dev = lambda a: torch.from_numpy(a).to("cuda")
+        dx, dy, de, dn = dev(x), dev(y), dev(east), dev(north)
+        out_s = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+        out_d = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+        N.check(lib.ssrs_interp_wind_nearest(N.ptr(dx), N.ptr(dy), N.ptr(de), N.ptr(dn), x.size, float(x0), float(y0),
+                                             float(res), rows, cols, N.ptr(out_s), N.ptr(out_d), N.current_stream()),
+                "ssrs_interp_wind_nearest")
+        return out_s, out_d
     tri = delaunay_triangles(x, y) if triangles is None else np.ascontiguousarray(triangles, dtype=np.int32)
     rows, cols = int(gridsize[0]), int(gridsize[1])
     dev = lambda a: torch.from_numpy(a).to("cuda")

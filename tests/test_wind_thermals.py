@@ -114,6 +114,33 @@ def test_gpu_thermals_distribution(golden):
 
 
 @pytest.mark.gpu
+def test_gpu_wind_interpolation_nearest(golden):
+    """Config.wtk_interp_type = 'nearest': every cell takes its closest site's wind, exactly the site griddata's k-d tree
+    returns (the interpolated value IS a site value, so the comparison is to float32 rounding, on every cell); the
+    filter that prunes the sites per CTA is exercised with few sites (fixture, ~25) and with many (3000 random ones,
+    dozens of survivors per CTA), and outside the sites' hull where the nearest site is far away."""
+    from ssrs_b200 import layers
+    g = golden("wind_thermals")
+    rows, cols, res, xg, yg = _grid(g)
+    rng = np.random.RandomState(3)
+    n = 3000
+    dense = (rng.uniform(-0.2, 0.6, n) * cols * res, rng.uniform(0.3, 1.2, n) * rows * res, rng.uniform(2.0, 14.0, n),
+             rng.uniform(0.0, 360.0, n))
+    for xl, yl, spd, drn in ((g["a_x"], g["a_y"], g["a_speed"], g["a_dirn"]), (g["b_x"], g["b_y"], g["b_speed"], g["b_dirn"]), dense):
+        ws, wd = layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), method='nearest')
+        ws, wd = ws.cpu().numpy().astype(np.float64), wd.cpu().numpy().astype(np.float64)
+        ref_s, ref_d = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg, method='nearest')
+        assert not np.isnan(ws).any() and not np.isnan(wd).any()
+        # a cell exactly between two sites may go either way in the tree: allow a handful of such cells
+        bad = np.abs(ws - ref_s) > 1e-6 * np.abs(ref_s).max()
+        dd = np.abs(wd - ref_d); dd = np.minimum(dd, 360.0 - dd)
+        bad |= dd > 1e-5 * 360.0
+        assert bad.sum() <= 2, bad.sum()
+    with pytest.raises(NotImplementedError):
+        layers.interpolate_wind_to_grid(g["a_x"], g["a_y"], g["a_speed"], g["a_dirn"], 0.0, 0.0, res, (rows, cols), method='cubic')
+
+
+@pytest.mark.gpu
 def test_gpu_wind_interpolation_full_size():
     """BASELINE config 4 shape: ~800 sites on a jittered 2 km lattice -> (5000, 6000) rasters; compared with
     griddata on every 40th grid line (griddata over all 3e7 cells takes minutes on the host)."""
@@ -138,3 +165,14 @@ def test_gpu_wind_interpolation_full_size():
     assert np.abs(got_s - ref_s).max() <= 1e-5 * ref_s.max()
     dd = np.abs(got_d - ref_d); dd = np.minimum(dd, 360.0 - dd)
     assert dd.max() <= 1e-5 * 360.0
+    # 'nearest' at the same size
+    layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), method='nearest')
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ws, wd = layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), method='nearest')
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"interpolate_wind_to_grid(nearest) {len(xl)} sites -> {rows}x{cols}: {dt * 1e3:.2f} ms")
+    ref_s, ref_d = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg, method='nearest')
+    got_s = ws[::40, ::40].cpu().numpy().astype(np.float64)
+    got_d = wd[::40, ::40].cpu().numpy().astype(np.float64)
+    dd = np.abs(got_d - ref_d); dd = np.minimum(dd, 360.0 - dd)
+    assert ((np.abs(got_s - ref_s) > 1e-6 * ref_s.max()) | (dd > 1e-5 * 360.0)).sum() <= 2
