@@ -620,8 +620,23 @@ SSRS_HD inline real ell_apply_fmt(const Ell& e, i64 i, const X& x) {
     const real xi = x(i);
     real acc = (real)0.0;
     i64 p = e.sptr[s] + (i & 31);
-    // four entries per trip: the column indices, then the gathers they address, are independent loads — a row's
-    // entries are otherwise a chain of dependent L2 round trips (the small levels are pure latency)
+    // eight, then four entries per trip: the entries, then the gathers they address, are independent loads — a row's
+    // entries are otherwise a chain of dependent L2 round trips (the small levels are pure latency).  Rows have ~10
+    // entries, so most rows cost two entry/gather round trips.
+    if (PACKED) {
+        for (; p + 224 < p1; p += 256) {
+            unsigned w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q] = e.pack[p + 32 * q];
+            real xs[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xs[q] = x(packed_col(w[q], i));
+            acc += ((packed_value(w[0]) * (xs[0] - xi) + packed_value(w[1]) * (xs[1] - xi)) +
+                    (packed_value(w[2]) * (xs[2] - xi) + packed_value(w[3]) * (xs[3] - xi))) +
+                   ((packed_value(w[4]) * (xs[4] - xi) + packed_value(w[5]) * (xs[5] - xi)) +
+                    (packed_value(w[6]) * (xs[6] - xi) + packed_value(w[7]) * (xs[7] - xi)));
+        }
+    }
     for (; p + 96 < p1; p += 128) {
         i64 c0, c1, c2, c3;
         float v0, v1, v2, v3;
