@@ -3,14 +3,15 @@
 // Replaces generate_simulated_tracks (ssrs/movmodel.py:264-318, one Python call per track mapped over a
 // fork pool at ssrs/simulator.py:360-369) and compute_presence_counts (ssrs/movmodel.py:410-419).
 //
-// One thread owns one track at a time and steps it to completion; when its track ends the lane
-// immediately takes the next unstarted track (lane-level refill), so warps stay full although track
-// lengths differ.  Per step a lane gathers the centre cell and the neighbours its direction-memory mask
-// allows from the interleaved {updraft, potential} raster (one 8-byte read-only load each), evaluates the
-// move probabilities in the reference's exact arithmetic (float32 potential differences, float64
-// everything else, numpy's pairwise-sum order), draws one uniform (caller-supplied in verification mode,
-// else counter-based Philox4x32-10 keyed by (seed, global track id, step)), and appends the new point:
-// a coalesced step-major int16x2 store and one `red.global.add.u32` on the presence raster.
+// One thread owns one track at a time and steps it to completion; when its track ends the lane takes the
+// next unstarted track from a device queue (lane-level refill inside one flat loop, see the kernel), so
+// warps stay as full as the heavy-tailed track lengths allow.  Per step a lane gathers the neighbours its
+// direction-memory mask allows from the interleaved {updraft, potential} raster (one 8-byte read-only load
+// each), evaluates the move probabilities — in the reference's exact arithmetic on request (float32
+// potential differences, float64 everything else, numpy's pairwise-sum order), else in an equivalent
+// division-free form —, draws one uniform (caller-supplied in verification mode, else counter-based
+// Philox4x32-10 keyed by (seed, global track id, step)), and appends the new point: a coalesced step-major
+// int16x2 store (optional) and one `red.global.add.u32` on the presence raster.
 //
 // This translation unit is compiled with -fmad=false: float64 products and sums must round separately
 // to reproduce numpy bit for bit.
