@@ -725,6 +725,7 @@ struct Hierarchy {
     int coarse_sweeps = 0;     // > 0: coarsest level too large for a dense inverse, Jacobi sweeps instead
     real omega = (real)0.8;        // Jacobi weight
     int nu = 1;                // pre- and post-smoothing sweeps
+    int nu_coarse = 1, nu_from = 1 << 30;   // experiment: nu_coarse sweeps on levels >= nu_from
     real overcorrect = (real)1.2;  // scale of the coarse-grid correction (plain aggregation under-corrects smooth error)
     FineWeights fw = {nullptr, nullptr};
     Fine32 f32;
@@ -935,16 +936,17 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
         i64 i0, i1;
         own_range(H, l, i0, i1);
         AMG_RC(exchange_ghosts(H, l, L.b32, sizeof(real)));
-        if (nu == 1 && H.fuse_coarse_first) { AMG_TRY(ell_first_residual32(e, i0, i1, L.b32, L.x32, L.r32, om, st)); }
+        const int nul = l >= H.nu_from ? H.nu_coarse : nu;
+        if (nul == 1 && H.fuse_coarse_first) { AMG_TRY(ell_first_residual32(e, i0, i1, L.b32, L.x32, L.r32, om, st)); }
         else {
             if (!first_done) AMG_TRY(ell_first32(e, i0, i1, L.b32, L.x32, om, st));
-            for (int s = 1; s < nu; ++s) {
+            for (int s = 1; s < nul; ++s) {
                 AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
                 AMG_TRY(level_jacobi(L, i0, i1, L.b32, L.x32, L.t32, om, st));
                 real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
             }
             // (the first sweep is elementwise, so the ghosts of x can be formed locally from the exchanged b)
-            if (nu == 1 && H.comm != nullptr && l < H.lrep) {
+            if (nul == 1 && H.comm != nullptr && l < H.lrep) {
                 const i64 g0 = L.ref_lo[H.rank], g1 = L.ref_hi[H.rank];
                 AMG_TRY(ell_first32(e, g0, i0, L.b32, L.x32, om, st));
                 AMG_TRY(ell_first32(e, i1, g1, L.b32, L.x32, om, st));
@@ -959,7 +961,8 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
         i64 i0, i1;
         own_range(H, l, i0, i1);
         AMG_TRY(prolong_add32(L, i0, i1, L.x32, H.lv[(size_t)l + 1].x32, H.overcorrect, st));
-        for (int s = 0; s < nu; ++s) {
+        const int nul = l >= H.nu_from ? H.nu_coarse : nu;
+        for (int s = 0; s < nul; ++s) {
             AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
             AMG_TRY(level_jacobi(L, i0, i1, L.b32, L.x32, L.t32, om, st));
             real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
@@ -1083,6 +1086,8 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     if (getenv("SSRS_X_OC")) H.overcorrect = (float)atof(getenv("SSRS_X_OC"));
     if (getenv("SSRS_X_OMEGA")) H.omega = (float)atof(getenv("SSRS_X_OMEGA"));
     if (getenv("SSRS_X_NU")) H.nu = atoi(getenv("SSRS_X_NU"));
+    if (getenv("SSRS_X_NUC")) H.nu_coarse = atoi(getenv("SSRS_X_NUC"));
+    if (getenv("SSRS_X_NUL")) H.nu_from = atoi(getenv("SSRS_X_NUL"));
     if (getenv("SSRS_X_FUSEC")) H.fuse_coarse_first = atoi(getenv("SSRS_X_FUSEC")) != 0;
 
     // Dirichlet nodes arrive as the reference's column-major ids (movmodel.py:25-29): i = col*nrow + row
