@@ -3,6 +3,7 @@ import ctypes
 import dataclasses
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -105,3 +106,19 @@ def test_assemble_matches_oracle_operator():
                     continue
                 i, j = c * nrow + r, (c + dc) * nrow + (r + dr)
                 assert dense[i, j] == g[d, r, c], (r, c, dr, dc)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's stdout contract: ONE JSON line, whatever libraries write to file descriptor 1 (it is re-pointed at
+    stderr for the run).  The reference arm runs on CPU; a small grid keeps it to a few seconds."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--rows", "300", "--cols", "400", "--resolution", "100", "--tracks-per-gpu", "2000"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "track-steps/sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
