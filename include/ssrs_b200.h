@@ -174,6 +174,9 @@ SSRS_API int ssrs_presence_allreduce(uint32_t* presence, int64_t n, const ssrs_c
  *         trajectory points (= steps + 1).   presence (optional): uint32 [rows][cols], incremented
  *         atomically (not cleared).   total_steps (optional): one uint64, incremented by the number
  *         of track-steps taken (loop iterations at ssrs/movmodel.py:285-317).
+ * Asynchronous on `stream`.  Tracks beyond the first per resident thread are handed out through a device counter
+ * (8 bytes per launch, taken from an 8 KB per-device array the library allocates on first use and zeroes on
+ * `stream`): which lane steps which track varies from run to run, the results do not (see above).
  */
 #define SSRS_STEP_EXACT 1
 
