@@ -115,7 +115,6 @@ struct FineGraph {
     int rows, cols;
     int interior_dirichlet;   // 1 if some Dirichlet node is more than one cell away from the border
     Parts parts;
-    const double* wd = nullptr;   // [4][n] precomputed forward link weights E, N, NE, NW (FineWeights::wd) once they exist
     SSRS_HD bool crosses(i64 i, i64 j) const { return parts_cross(parts, i, j); }
     SSRS_HD i64 size() const { return (i64)rows * cols; }
     SSRS_HD bool excluded(i64 i) const { return sign_set(kd[i]); }
@@ -128,22 +127,10 @@ struct FineGraph {
         if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) return E_SKIP;          // movmodel.py:75
         j = (i64)rr * cols + cc;
         const float kj = kd[j];
-        const bool quirk = c == cols - 1 && r >= 1 && r <= rows - 2 && dr == -1;  // :73-79 last-column quirk
-        if (wd != nullptr && !quirk) {
-            // the link's weight is the forward weight of whichever end sees it as E, N, NE or NW: one load instead of
-            // a float64 division (setup passes scan all eight links of every node several times)
-            const i64 n = (i64)rows * cols;
-            const bool fwd = dr > 0 || (dr == 0 && dc > 0);
-            const i64 at = fwd ? i : j;
-            const int ddc = fwd ? dc : -dc;                                        // seen from the end that owns it
-            const int slot = (dr == 0) ? 0 : (ddc == 0 ? 1 : (ddc > 0 ? 2 : 3));   // E | N | NE | NW
-            a = -wd[slot * n + at];
-            return sign_set(kj) ? E_DIR : E_OFF;
-        }
         const double ka = fabs((double)kd[i]), kb = fabs((double)kj);
         const double hm = (ka == 0.0 || kb == 0.0) ? HM_FLOOR : 2.0 * ka * kb / (ka + kb);   // :442-447
         bool diagonal = (dr != 0) && (dc != 0);
-        if (quirk) {
+        if (c == cols - 1 && r >= 1 && r <= rows - 2 && dr == -1) {               // :73-79 last-column quirk
             if (dc == 0) diagonal = true;
             else if (dc == -1) diagonal = false;
         }
@@ -1180,7 +1167,6 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             wdd[i] = bf16_bits((float)ne) | (bf16_bits((float)nw) << 16);
         }));
         H.fw.wf = nullptr; H.fw.wd = wd;
-        H.fine.wd = wd;                 // from here on the setup passes read link weights instead of recomputing them
         Fine32 F;
         F.w.en.p = wen; F.w.dd.p = wdd; F.dinv = dinv; F.kd = kd; F.rows = rows; F.cols = cols;
         const float *fE = wf, *fN = wf + n, *fNE = wf + 2 * n, *fNW = wf + 3 * n;
