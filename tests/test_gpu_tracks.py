@@ -138,6 +138,43 @@ def test_track_queue_matches_c_oracle():
         assert np.array_equal(res.presence.cpu().numpy(), ref["presence"])
 
 
+def test_move_limit_and_tiny_inputs():
+    """Tracks that never leave: a bowl-shaped potential keeps many tracks circling until max_moves = rows/2 * cols/2
+    (movmodel.py:277, :285) — the fast lane's budget has to stop them at exactly that step.  Lengths, presence and the
+    step total equal the C oracle's; then the degenerate inputs: no tracks at all, one track, the smallest grid."""
+    from ssrs_b200 import movmodel as mm
+    rows, cols = 48, 64
+    yy, xx = np.mgrid[0:rows, 0:cols].astype(np.float32)
+    P = (((yy - rows / 2) ** 2 + (xx - cols / 2) ** 2) * 0.5).astype(np.float32)
+    rng = np.random.RandomState(2)
+    U = (0.2 + rng.rand(rows, cols)).astype(np.float32)
+    n = 4000
+    starts = np.stack([rng.randint(2, rows - 2, n), rng.randint(2, cols - 2, n)], 1).astype(np.int32)
+    ref = OC.step_tracks(U, P, (rows, cols), starts, 0.0, 1, 1.0, seed=3, nthreads=8, fast=True)
+    kmax = int(np.ceil(rows / 2 * cols / 2))
+    assert (ref["traj_len"] - 1 >= kmax).sum() > 100                   # the case does exercise the limit
+    res = mm.simulate_tracks_batch(0.0, starts[:, 0], starts[:, 1], (rows, cols), 1, 1.0, updraft_field=U, potential_field=P,
+                                   seed=3)
+    assert res.total_steps == ref["total_steps"]
+    assert np.array_equal(res.traj_len.cpu().numpy(), ref["traj_len"])
+    assert np.array_equal(res.presence.cpu().numpy(), ref["presence"])
+    assert int(res.traj_len.max().item()) == kmax + 1
+    # no tracks: nothing happens, nothing fails
+    empty = mm.simulate_tracks_batch(0.0, starts[:0, 0], starts[:0, 1], (rows, cols), 1, 1.0, updraft_field=U,
+                                     potential_field=P, seed=3)
+    assert empty.total_steps == 0 and int(empty.presence.sum().item()) == 0
+    # one track; and the smallest grid the ABI accepts (5 x 5: every cell is next to the border)
+    one = mm.simulate_tracks_batch(0.0, starts[:1, 0], starts[:1, 1], (rows, cols), 1, 1.0, updraft_field=U, potential_field=P,
+                                   seed=3)
+    assert int(one.traj_len[0].item()) == int(ref["traj_len"][0])
+    U5, P5 = U[:5, :5].copy(), np.ascontiguousarray(P[:5, :5])
+    s5 = np.array([[2, 2], [1, 3], [3, 1]], dtype=np.int32)
+    ref5 = OC.step_tracks(U5, P5, (5, 5), s5, 0.0, 1, 1.0, seed=9, nthreads=1, fast=True)
+    got5 = mm.simulate_tracks_batch(0.0, s5[:, 0], s5[:, 1], (5, 5), 1, 1.0, updraft_field=U5, potential_field=P5, seed=9)
+    assert np.array_equal(got5.traj_len.cpu().numpy(), ref5["traj_len"])
+    assert np.array_equal(got5.presence.cpu().numpy(), ref5["presence"])
+
+
 def test_sharding_invariance():
     """Tracks block-partitioned over 1/2/4/8 shards (what each GPU of a box would run) give bit-identical
     summed presence and per-track lengths: the RNG is keyed by the global track id."""
