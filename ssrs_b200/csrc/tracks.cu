@@ -289,9 +289,11 @@ __device__ __forceinline__ unsigned flat_of(unsigned slot) { return slot + (slot
 
 // One fast-lane step: choose_fast3<true, true> with the selection made branch-free and the new centre's fields taken
 // from the chosen candidate's registers instead of a fourth gather.
-//   * d_i NaN or no d_i > 0  <=>  choose_fast3's (any_nan || all q == 0): the weights become the directional ones
-//     (q_i == 0 exactly when d_i <= 0, because the clipped updrafts are >= 1e-6);
-//   * max(d_i, 0) replaces `d_i > 0 ? ... : 0`: the product is the same for d_i > 0 and a zero otherwise;
+//   * max.NaN(d_i, 0) replaces `d_i > 0 ? ... : 0`: the product is the same for d_i > 0, a zero for d_i <= 0 and NaN
+//     for a NaN difference (q_i == 0 exactly when d_i <= 0, because the clipped updrafts are >= 1e-6);
+//   * d_i NaN or no d_i > 0  <=>  choose_fast3's (any_nan || all q == 0): then c2 is NaN or zero, `c2 > target` fails,
+//     and the directional weights are handled off the main line (11 % of the steps; a lone lane — the end of every
+//     launch — saves their two table loads and six selects on the other 89 %);
 //   * when c2 > target the chosen move is the first running sum above the target — the same three comparisons; every
 //     other case (weights all zero after the fallback, u * c2 rounding up to c2, a NaN or infinite updraft) goes to
 //     the out-of-line copy of the original code.  Same draws, same arithmetic: bit-identical trajectories.
@@ -301,18 +303,15 @@ __device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& l
     const float4 nv = lut.ninv[slot];
     // 32-bit cell indices (rows * cols < 2^31): one IMAD.WIDE per address
     const float2 f0 = __ldg(P.fields + (lin + cand.x)), f1 = __ldg(P.fields + (lin + cand.y)), f2 = __ldg(P.fields + (lin + cand.z));
-    const double2 dir01 = lut.dir01[slot];
-    const double dir2 = lut.dir2[slot];
     const float d0 = __fmul_rn(__fsub_rn(fc.y, f0.y), nv.x);            // float32, movmodel.py:301-304
     const float d1 = __fmul_rn(__fsub_rn(fc.y, f1.y), nv.y);
     const float d2 = __fmul_rn(__fsub_rn(fc.y, f2.y), nv.z);
-    const bool use_dir = !(fmax_nan(fmax_nan(d0, d1), d2) > 0.0f);
     const double u0 = clip_updraft(f0.x), u1 = clip_updraft(f1.x), u2 = clip_updraft(f2.x);
     const double s0 = uc + u0, s1 = uc + u1, s2 = uc + u2;
-    double q0 = ((double)fmaxf(d0, 0.0f) * u0) * (s1 * s2);
-    double q1 = ((double)fmaxf(d1, 0.0f) * u1) * (s0 * s2);
-    double q2 = ((double)fmaxf(d2, 0.0f) * u2) * (s0 * s1);
-    if (use_dir) { q0 = dir01.x; q1 = dir01.y; q2 = dir2; }
+    // max.NaN: a NaN potential difference makes its weight, and with it c2, NaN and sends the step to the else branch
+    const double q0 = ((double)fmax_nan(d0, 0.0f) * u0) * (s1 * s2);
+    const double q1 = ((double)fmax_nan(d1, 0.0f) * u1) * (s0 * s2);
+    const double q2 = ((double)fmax_nan(d2, 0.0f) * u2) * (s0 * s1);
     const double c1 = q0 + q1, c2 = c1 + q2;
     const double target = u * c2;
     if (c2 > target) {
@@ -322,26 +321,42 @@ __device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& l
         fc = a ? f0 : (b ? f1 : f2);
         uc = a ? u0 : (b ? u1 : u2);
     } else {
-        int idx;
-        if (use_dir && c2 == 0.0) {
-            // the candidates' directional weights are zero as well (a track heading away from track_direction in a
-            // potential minimum, ~1 % of all steps): the reference drops the mask and draws from all nine directional
-            // weights (movmodel.py:239-240).  That distribution does not depend on the cell: first flat index whose
-            // running sum exceeds u * total, exactly what choose_fast_general<false>(mask 0) evaluates.
-            const double tg = u * lut.drun[8];
-            int cnt = 0;
+        // c2 is zero (no candidate lies lower: 11 % of all steps), NaN, or u * c2 rounded up to c2
+        int idx = -1;
+        if (!(fmax_nan(fmax_nan(d0, d1), d2) > 0.0f)) {
+            // choose_fast3's (any_nan || all q == 0): the candidates' directional weights (movmodel.py:234-236)
+            const double2 dir01 = lut.dir01[slot];
+            const double dir2 = lut.dir2[slot];
+            const double e1 = dir01.x + dir01.y, e2 = e1 + dir2;
+            const double tg = u * e2;
+            if (e2 > tg) {
+                const bool a = dir01.x > tg, b = e1 > tg;
+                lin += a ? cand.x : (b ? cand.y : cand.z);
+                slot = ((unsigned)cand.w >> (a ? 0 : (b ? 4 : 8))) & 15u;
+                fc = a ? f0 : (b ? f1 : f2);
+                uc = a ? u0 : (b ? u1 : u2);
+            } else if (e2 == 0.0) {
+                // those are zero as well (a track heading away from track_direction in a potential minimum, ~1 % of all
+                // steps): the reference drops the mask and draws from all nine directional weights (movmodel.py:239-240).
+                // That distribution does not depend on the cell: first flat index whose running sum exceeds u * total,
+                // exactly what choose_fast_general<false>(mask 0) evaluates.
+                const double tg9 = u * lut.drun[8];
+                int cnt = 0;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) cnt += (lut.drun[i] > tg) ? 0 : 1;       // running sums are non-decreasing
-            idx = cnt < 9 ? cnt : lut.dlast;
-        } else {
+                for (int i = 0; i < 9; ++i) cnt += (lut.drun[i] > tg9) ? 0 : 1;   // running sums are non-decreasing
+                idx = cnt < 9 ? cnt : lut.dlast;
+            } else idx = -2;
+        } else idx = -2;
+        if (idx == -2)
             idx = choose_fast3_rare(P, P.fields + lin, nc, (int)flat_of(cand.w & 15), (int)flat_of((cand.w >> 4) & 15),
                                     (int)flat_of((cand.w >> 8) & 15), fc, f0, f1, f2, u);
+        if (idx >= 0) {
+            const int dr = ((idx * 11) >> 5) - 1, dc = idx - 3 * (dr + 1) - 1;
+            lin += dr * nc + dc;
+            slot = slot_of((unsigned)idx);
+            fc = __ldg(P.fields + lin);
+            uc = clip_updraft(fc.x);
         }
-        const int dr = ((idx * 11) >> 5) - 1, dc = idx - 3 * (dr + 1) - 1;
-        lin += dr * nc + dc;
-        slot = slot_of((unsigned)idx);
-        fc = __ldg(P.fields + lin);
-        uc = clip_updraft(fc.x);
     }
     red_add1(P.presence + lin);
 }
