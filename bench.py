@@ -44,9 +44,9 @@ UNIT = "track-steps/s"
 STEP_BYTES = 76          # 72 B of 3x3 gathers on two f32 fields + 4 B presence atomic (no trajectory store)
 STENCIL_BYTES = 20       # 4 B DEM + 4 outputs x 4 B
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_tracks_kernel launch of the default workload, from the
-# `ncu --set full` capture of this command (profiles/r01_ncu_step_tracks_v8.txt): 621.6 MB + 160.7 MB.  Far below
-# the 78.5 GB of algorithmic gather bytes: the gathers are served by L1 (43 % hits) and L2 (81 % hits).
-STEP_TRAFFIC_DEFAULT = 782.2e6
+# `ncu --set full` capture of this command (profiles/r01_ncu_step_tracks_v12.txt): 559.7 MB + 149.4 MB.  Far below
+# the 77.5 GB of algorithmic gather bytes: the gathers are served by L1 (44 % hits) and L2 (82 % hits).
+STEP_TRAFFIC_DEFAULT = 709.1e6
 
 
 def parse():
@@ -244,7 +244,9 @@ def main():
     for i in range(a.steps):
         presence.zero_()
         kev[i][0].record()
-        mm.simulate_tracks_batch(0.0, sr, sc, shape, fields=fields, seed=a.seed, track_id0=rank * n_per,
+        # every timed step is another realisation of the same workload (seed + 1 + step): a launch lasts as long as its
+        # longest track, and one realisation's maximum (90k..104k steps) would decide the whole figure
+        mm.simulate_tracks_batch(0.0, sr, sc, shape, fields=fields, seed=a.seed + 1 + i, track_id0=rank * n_per,
                                  presence=presence, total_steps=total)
         kev[i][1].record()
         if world > 1:
@@ -275,11 +277,11 @@ def main():
     start_h = np.stack([sr, sc], 1)
     tot_e2e = torch.zeros(1, dtype=torch.int64, device="cuda")
 
-    def e2e_step():
+    def e2e_step(i=-1):
         u_d = up_h.to("cuda", non_blocking=True)
         p_d = pot_h.to("cuda", non_blocking=True)
         r = mm.simulate_tracks_batch(0.0, start_h[:, 0], start_h[:, 1], shape, updraft_field=u_d, potential_field=p_d,
-                                     seed=a.seed, track_id0=rank * n_per, total_steps=tot_e2e)
+                                     seed=a.seed + 1 + i, track_id0=rank * n_per, total_steps=tot_e2e)
         if world > 1:
             D.presence_allreduce(r.presence)
         pres_h.copy_(r.presence, non_blocking=True)
@@ -291,8 +293,8 @@ def main():
     tot_e2e.zero_()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(a.steps):
-        e2e_step()
+    for i in range(a.steps):
+        e2e_step(i)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -317,7 +319,7 @@ def main():
             "dtype": "f64 probabilities on f32 fields", "data": "synthetic",
             "config": {"workload": workload_name(a, world), "grid": [a.rows, a.cols], "tracks_per_gpu": n_per,
                        "track_steps_per_step": steps_all / a.steps, "l2": "inputs_exceed_l2 (fields 240 MB > 126 MB)",
-                       "rng": "philox4x32-10 keyed by (seed, global track id, step)",
+                       "rng": "philox4x32-10 keyed by (seed, global track id, step); timed step i uses seed + 1 + i (another realisation per step)",
                        "parallelism": f"tracks sharded over {world} GPU(s), fields replicated, presence all-reduce"},
             "fields": finfo,
             "roofline": {"bound": "hbm", "kernel": "step_tracks_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -326,7 +328,7 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "peak_source": peak_src,
                          "bytes_per_track_step": STEP_BYTES, "kernel_ms": kernel_ms,
-                         "note": "not HBM-bound by construction (SURVEY §8d): gathers hit L1/L2 (ncu: L2 hit 81 %, DRAM throughput 0.2 %); "
+                         "note": "not HBM-bound by construction (SURVEY §8d): gathers hit L1/L2 (ncu: L2 hit 82 %, DRAM throughput 0.2 %); "
                                  "the launch lasts as long as its longest track (instruction-latency bound tail); "
                                  "HBM fraction reported as the contract asks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
