@@ -1,9 +1,4 @@
-"""Per-step latency of the stepping kernel (kernel time / longest track) and bulk throughput, on the bench fields.
-
-The launch time at 100k tracks is set by the longest track, and which track that is depends on the last bits of the
-potential, so kernel A/B comparisons need the SAME fields: `--save-fields DIR` writes the updraft and
-potential rasters of this run as .npy (e.g. into gpurun_out/, then copy them to tools/_fields/, which is git-ignored
-but travels to the GPU box), `--fields DIR` steps on stored rasters instead of solving again."""
+"""Per-step latency of the stepping kernel (kernel time / longest track) and bulk throughput, on the bench fields."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -12,18 +7,7 @@ from ssrs_b200 import movmodel as mm
 class A: pass
 a = A(); a.rows = 5000; a.cols = 6000; a.resolution = 10.0; a.tracks_per_gpu = 100000; a.seed = 2021; a.no_solve = False
 sr, sc = bench.start_cells(a, 1_000_000)
-_args = sys.argv[1:]
-if "--fields" in _args:
-    d = _args[_args.index("--fields") + 1]
-    up = torch.from_numpy(np.load(os.path.join(d, "updraft_5000x6000.npy"))).cuda()
-    pot = torch.from_numpy(np.load(os.path.join(d, "potential_5000x6000.npy"))).cuda()
-else:
-    up, pot, info = bench.build_fields_gpu(a, torch)
-if "--save-fields" in _args:
-    d = _args[_args.index("--save-fields") + 1]
-    os.makedirs(d, exist_ok=True)
-    np.save(os.path.join(d, "updraft_5000x6000.npy"), up.cpu().numpy())
-    np.save(os.path.join(d, "potential_5000x6000.npy"), pot.cpu().numpy())
+up, pot, info = bench.build_fields_gpu(a, torch)
 f = mm.interleave_fields(up, pot)
 def run(n, exact=False, reps=3):
     best = 1e9
