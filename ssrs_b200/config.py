@@ -30,18 +30,18 @@ class Config:
     run_name: str = 'default'
     out_dir: str = os.path.join(os.path.abspath(os.path.curdir), 'output')
     max_cores: int = 8                     # kept for compatibility; the GPU path has no process pool
-    sim_seed: int = -1
+    sim_seed: int = -1                     # >= 0: seeds numpy (starting cells) and keys the stepper's Philox streams
     sim_mode: str = 'uniform'              # 'uniform' | 'snapshot' | 'seasonal'
     print_verbose: bool = False
 
     # -- terrain
     southwest_lonlat: Tuple[float, float] = (-106.21, 42.78)
     projected_crs: str = 'ESRI:102008'
-    region_width_km: Tuple[float, float] = (60., 50.)
-    resolution: int = 100.
+    region_width_km: Tuple[float, float] = (60., 50.)     # with `resolution`: gridsize = (rows, cols) of every raster
+    resolution: int = 100.                 # metres per cell (stage 1 stencil spacing; 10 m -> 5000 x 6000 cells)
 
     # -- uniform mode (direction: northerly 0, easterly 90, westerly 270)
-    uniform_winddirn: float = 270.
+    uniform_winddirn: float = 270.         # scalar wind of `ssrs_updraft` in uniform mode
     uniform_windspeed: float = 10.
 
     # -- snapshot mode
@@ -57,20 +57,20 @@ class Config:
     wtk_source: str = 'AWS'
     wtk_orographic_height: int = 100
     wtk_thermal_height: int = 100
-    wtk_interp_type: str = 'linear'
+    wtk_interp_type: str = 'linear'        # site -> grid: 'linear' (ssrs_interp_wind) | 'nearest' (ssrs_interp_wind_nearest)
 
     # -- updraft
-    thermals_realization_count: bool = 0
-    updraft_threshold: float = 0.75
-    movement_model: str = 'fluidflow'      # 'fluidflow' | 'drw'
+    thermals_realization_count: bool = 0   # > 0: that many extra (updraft, potential, tracks) triples per wind case
+    updraft_threshold: float = 0.75        # `thr` of get_above_threshold_speed, fused into the stencil kernel
+    movement_model: str = 'fluidflow'      # 'fluidflow' (potential solve + field-driven steps) | 'drw' (no fields)
 
     # -- tracks
-    track_direction: float = 0
-    track_count: str = 1000
+    track_direction: float = 0             # degrees; picks the Dirichlet sets of the solve and the directional weights
+    track_count: str = 1000                # tracks per (wind case, realisation) = one `ssrs_step_tracks` launch per GPU
     track_start_region: Tuple[float, float, float, float] = (5, 55, 1, 2)
     track_start_type: str = 'random'       # 'structured' | 'random'
-    track_stochastic_nu: float = 1.
-    track_dirn_restrict: int = 1
+    track_stochastic_nu: float = 1.        # exponent on the move probabilities; != 1 takes the general step, not the fast lane
+    track_dirn_restrict: int = 1           # direction memory (0 = whole history, <= 16); 1 is the fast lane's case
 
     # -- turbines / plotting
     turbine_minimum_hubheight: float = 50.
