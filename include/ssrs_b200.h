@@ -163,7 +163,9 @@ SSRS_API int ssrs_presence_allreduce(uint32_t* presence, int64_t n, const ssrs_c
  *         (ssrs/movmodel.py:247-257), computed by the caller exactly as the reference does.
  * memory, nu: track_dirn_restrict and track_stochastic_nu (ssrs/config.py:56-57).
  * Random numbers: if uniforms != NULL ("verification mode") step k of track t consumes
- *         uniforms[t*uniforms_stride + k] — the reference's pre-drawn np.random stream; otherwise
+ *         uniforms[t*uniforms_stride + k] — the reference's pre-drawn np.random stream (uniforms_stride must cover
+ *         the longest track: a track that needs step k >= uniforms_stride stops there and reports
+ *         traj_len[t] = -(points so far), so the caller can retry with a longer stream); otherwise
  *         Philox4x32-10 keyed by seed with counter (track_id0 + t, k), so results do not depend on
  *         how tracks are sharded over GPUs.
  * flags: 0, or SSRS_STEP_EXACT to evaluate the probabilities in the reference's exact operation order

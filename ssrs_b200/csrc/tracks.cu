@@ -93,20 +93,19 @@ __device__ __forceinline__ int choose_exact(const TrackParams& P, const float2* 
         const double iuc = 1.0 / uc;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            p[i] = 0.0;
-            if (i != 4 && ((mask >> i) & 1u)) {
-                const int dr = i / 3 - 1, dc = i % 3 - 1;
-                const float2 f = __ldg(base + dr * nc + dc);
-                const double ui = fmax((double)f.x, 1e-06);
-                const double w = 2.0 / (iuc + 1.0 / ui);                // :296, :260-261
-                const float ninv = (dr != 0 && dc != 0) ? NINV_D : 1.0f;
-                const float d = __fmul_rn(__fsub_rn(fc.y, f.y), ninv);  // float32, :301-304
-                double v = w * (double)d;                               // :305
-                any_nan |= (v != v);
-                v = v > 0.0 ? v : 0.0;                                  // clip(min=0), :231
-                p[i] = v;
-                any_nz |= (v != 0.0);
-            }
+            // all nine entries, masked or not, like the reference: its NaN test (:228) sees the whole 3x3 patch
+            const int dr = i / 3 - 1, dc = i % 3 - 1;
+            const float2 f = __ldg(base + dr * nc + dc);
+            const double ui = fmax((double)f.x, 1e-06);
+            const double w = 2.0 / (iuc + 1.0 / ui);                    // :296, :260-261
+            const float ninv = (i == 4) ? 0.0f : ((dr != 0 && dc != 0) ? NINV_D : 1.0f);
+            const float d = __fmul_rn(__fsub_rn(fc.y, f.y), ninv);      // float32, :301-304
+            double v = w * (double)d;                                   // :305
+            any_nan |= (v != v);
+            v = v > 0.0 ? v : 0.0;                                      // clip(min=0), :231
+            if (i == 4 || !((mask >> i) & 1u)) v = 0.0;                 // :232-233
+            p[i] = v;
+            any_nz |= (v != 0.0);
         }
     } else {
 #pragma unroll
@@ -508,6 +507,15 @@ __global__ void __launch_bounds__(128, 6) step_tracks_kernel(const TrackParams P
                         // one uniform per step (:312)
                         double u;
                         if (P.uniforms != nullptr) {
+                            // verification mode: a track that outlives the caller's stream stops here and reports a
+                            // negative length (-(points so far)); the host retries with a longer stream
+                            if ((long long)k >= P.ustride) {
+                                if (P.traj_len != nullptr) P.traj_len[t] = -(k + 1);
+                                steps_local += (unsigned long long)k;
+                                alive = false;
+                                t = stride + (long long)atomicAdd(P.next_track, 1ULL);
+                                continue;
+                            }
                             u = __ldg(P.uniforms + t * P.ustride + k);
                         } else {
                             // Philox4x32-10 yields four words = two uniforms: counter (gid, k >> 1), words {0,1} for even k,

@@ -148,26 +148,29 @@ class TrackBatchResult:
     def total_steps(self) -> int:
         return int(self._total.item())
 
-    def tracks(self) -> List[np.ndarray]:
-        """List of int16 [L, 2] arrays like the reference's pool.map result (:318)."""
+    def _checked_lengths(self):
         if self.traj is None:
             raise ValueError("trajectories were not recorded (record=False)")
         lens = self.traj_len.cpu().numpy()
+        if (lens < 0).any():
+            raise ValueError("the supplied uniforms were shorter than the longest track (negative traj_len)")
         if (lens > self.traj_cap).any():
-            raise ValueError("traj_cap was smaller than the longest track")
+            raise ValueError("traj_cap was smaller than the longest track; leave traj_cap=None (two-pass recording) "
+                             "or use record_tracks_packed")
+        return lens
+
+    def tracks(self) -> List[np.ndarray]:
+        """List of int16 [L, 2] arrays like the reference's pool.map result (:318)."""
+        lens = self._checked_lengths()
         tr = self.traj.permute(1, 0, 2).contiguous().cpu().numpy()
         return [tr[i, :lens[i]].copy() for i in range(self.n_tracks)]
-
 
     def packed(self):
         """(offsets int64 [n + 1], points int16 [total, 2]) on the host — the packed on-disk form (trackio.py),
         gathered on the device from the step-major trajectory buffer."""
         torch = N.require_cuda()
-        if self.traj is None:
-            raise ValueError("trajectories were not recorded (record=False)")
+        self._checked_lengths()
         lens = self.traj_len.to(torch.int64)
-        if bool((lens > self.traj_cap).any()):
-            raise ValueError("traj_cap was smaller than the longest track")
         offsets = torch.zeros(self.n_tracks + 1, dtype=torch.int64, device=lens.device)
         torch.cumsum(lens, 0, out=offsets[1:])
         points_parts = []
@@ -199,6 +202,17 @@ def _f32_cuda(a, torch):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to("cuda")
 
 
+TRAJ_BUFFER_BYTES = 2 << 30        # device budget of one step-major trajectory buffer (4 B x cap x tracks)
+
+
+def _launch_steps(fields, rows, cols, start, n, track_id0, dirp_c, memory, nu, seed, u_t, ustride, traj, cap, traj_len,
+                  presence, total_steps, exact):
+    N.check(N.load().ssrs_step_tracks(N.ptr(fields), rows, cols, N.ptr(start), n, int(track_id0), dirp_c, int(memory),
+                                      float(nu), int(seed) & (2 ** 64 - 1), N.ptr(u_t), ustride, N.ptr(traj), cap,
+                                      N.ptr(traj_len), N.ptr(presence), N.ptr(total_steps), 1 if exact else 0,
+                                      N.current_stream()), "ssrs_step_tracks")
+
+
 def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, memory_parameter: int = 1,
                           scaling_parameter: float = 1.0, fields=None, updraft_field=None, potential_field=None,
                           seed: int = 0, track_id0: int = 0, uniforms=None, record: bool = False,
@@ -212,9 +226,14 @@ def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, 
     (seed, track_id0 + i, step).  `exact=True` forces the reference's exact operation order in production mode
     (verification mode always uses it).  `presence` (int32 CUDA tensor [rows, cols]) is accumulated into if given,
     else a fresh raster is created.
+    `record=True` stores the trajectories (step-major int16 [cap, n, 2]).  Track lengths are heavy-tailed (the longest
+    of 100k tracks on 5000 x 6000 cells has ~1e5 points against a mean of 1e4), so without an explicit `traj_cap` the
+    recording is two-pass: a first launch without trajectory or presence output yields the exact lengths (the random
+    streams are counter-based or caller-supplied, so the second launch repeats it step for step), the second records
+    with cap = longest track.  For batches whose buffer would exceed TRAJ_BUFFER_BYTES use `record_tracks_packed`.
     """
     torch = N.require_cuda()
-    lib = N.load()
+    N.load()
     rows, cols = int(grid_shape[0]), int(grid_shape[1])
     sr = np.asarray(start_rows).astype(np.int64).ravel()
     sc = np.asarray(start_cols).astype(np.int64).ravel()
@@ -238,21 +257,64 @@ def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, 
         if un.ndim != 2 or un.shape[0] != n:
             raise ValueError("uniforms must be [n_tracks, stride]")
         u_t, ustride = torch.from_numpy(un).to("cuda"), un.shape[1]
+    traj_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+    common = (fields, rows, cols, start, n, track_id0, dirp_c, memory_parameter, scaling_parameter, seed, u_t, ustride)
     traj = None
     cap = 0
     if record:
-        cap = int(traj_cap) if traj_cap else int(4 * max(rows, cols))
+        if traj_cap:
+            cap = int(traj_cap)
+        else:
+            _launch_steps(*common, None, 0, traj_len, None, None, exact)            # pass 1: lengths only
+            cap = max(1, int(traj_len.abs().max().item())) if n else 1
+            if 4 * cap * n > TRAJ_BUFFER_BYTES:
+                raise ValueError(f"recording {n} tracks (longest {cap} points) needs a {4 * cap * n / 2 ** 30:.1f} GiB "
+                                 f"trajectory buffer; use record_tracks_packed (chunked) or pass traj_cap explicitly")
         traj = torch.zeros((cap, n, 2), dtype=torch.int16, device="cuda")
-    traj_len = torch.zeros(n, dtype=torch.int32, device="cuda")
     if presence is None:
         presence = torch.zeros((rows, cols), dtype=torch.int32, device="cuda")
     if total_steps is None:
         total_steps = torch.zeros(1, dtype=torch.int64, device="cuda")
-    N.check(lib.ssrs_step_tracks(N.ptr(fields), rows, cols, N.ptr(start), n, int(track_id0), dirp_c,
-                                 int(memory_parameter), float(scaling_parameter), int(seed) & (2 ** 64 - 1),
-                                 N.ptr(u_t), ustride, N.ptr(traj), cap, N.ptr(traj_len), N.ptr(presence),
-                                 N.ptr(total_steps), 1 if exact else 0, N.current_stream()), "ssrs_step_tracks")
+    _launch_steps(*common, traj, cap, traj_len, presence, total_steps, exact)
     return TrackBatchResult(n, (rows, cols), traj, traj_len, presence, total_steps, cap)
+
+
+def record_tracks_packed(move_dirn: float, start_rows, start_cols, grid_shape, memory_parameter: int = 1,
+                         scaling_parameter: float = 1.0, fields=None, seed: int = 0, track_id0: int = 0,
+                         lengths=None, exact: bool = False, buffer_bytes: int = TRAJ_BUFFER_BYTES):
+    """Trajectories of a large batch as (offsets int64 [n + 1], points int16 [total, 2]) on the host, recorded in
+    contiguous chunks of track ids sized so that every chunk's step-major buffer (4 B x its longest track x its
+    tracks) stays below `buffer_bytes`.  `lengths` (int array [n], points per track) from a previous
+    `simulate_tracks_batch(...).traj_len` of the same (seed, track_id0) saves the measuring launch.  Presence is not
+    accumulated here (the counting launch already did); Philox streams make every relaunch identical."""
+    sr = np.asarray(start_rows).astype(np.int64).ravel()
+    sc = np.asarray(start_cols).astype(np.int64).ravel()
+    n = sr.size
+    if lengths is None:
+        res = simulate_tracks_batch(move_dirn, sr, sc, grid_shape, memory_parameter, scaling_parameter, fields=fields,
+                                    seed=seed, track_id0=track_id0, exact=exact)
+        lengths = res.traj_len.cpu().numpy()
+    lengths = np.asarray(lengths, dtype=np.int64)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    points = np.empty((int(offsets[-1]), 2), dtype=np.int16)
+    lo = 0
+    while lo < n:
+        hi, cap = lo, 0
+        while hi < n and 4 * max(cap, int(lengths[hi])) * (hi - lo + 1) <= buffer_bytes:
+            cap = max(cap, int(lengths[hi]))
+            hi += 1
+        if hi == lo:                                    # one track longer than the whole budget: record it alone
+            cap, hi = int(lengths[lo]), lo + 1
+        res = simulate_tracks_batch(move_dirn, sr[lo:hi], sc[lo:hi], grid_shape, memory_parameter, scaling_parameter,
+                                    fields=fields, seed=seed, track_id0=track_id0 + lo, record=True, traj_cap=cap,
+                                    exact=exact)
+        off_c, pts_c = res.packed()
+        if not np.array_equal(off_c[1:] - off_c[:-1], lengths[lo:hi]):
+            raise RuntimeError("record_tracks_packed: relaunch produced different track lengths")
+        points[offsets[lo]:offsets[hi]] = pts_c
+        lo = hi
+    return offsets, points
 
 
 def generate_simulated_tracks(move_dirn: float, start_location, grid_shape, memory_parameter: int = 1,
@@ -262,16 +324,16 @@ def generate_simulated_tracks(move_dirn: float, start_location, grid_shape, memo
     reference's trajectory when given the same float32 fields."""
     rows, cols = int(grid_shape[0]), int(grid_shape[1])
     chunk = int(4 * max(rows, cols))
-    max_moves = rows / 2 * cols / 2
     state = np.random.get_state()
     while True:
         np.random.set_state(state)
         u = np.random.random_sample(chunk)[None, :]
+        # a track that needs more than `chunk` uniforms stops at the end of the stream and reports a negative length
         res = simulate_tracks_batch(move_dirn, [start_location[0]], [start_location[1]], grid_shape, memory_parameter,
                                     scaling_parameter, updraft_field=updraft_field, potential_field=potential_field,
                                     uniforms=u, record=True, traj_cap=chunk + 1)
         length = int(res.traj_len.cpu().numpy()[0])
-        if length - 1 < chunk or length - 1 >= max_moves:
+        if length > 0:
             break
         chunk *= 4
     np.random.set_state(state)

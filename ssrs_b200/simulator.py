@@ -22,6 +22,11 @@ constructor always downloads terrain; here it is injected with keyword-only exte
                  interpolated to the terrain grid on the GPU like the reference's griddata(linear) recipe
     wind_points= (xlocs, ylocs) projected site coordinates (the reference's get_wtk_locs())
     bounds=      projected bounds (west, south, east, north); default puts the south-west corner at (0, 0)
+    force_potential=True   recompute every potential even if `<id>_potential.npy` exists.  Independently of it a cached
+                 potential is only reused when the content key stored beside it (`<id>_potential.key`: a hash of the
+                 thresholded updraft the solve would consume, the movement direction and the grid) matches — the
+                 reference's cache (`simulator.py:264-272`) is keyed by the id string alone and silently reuses a
+                 potential computed for other terrain or wind; a file without a key counts as stale.
 When `torch.distributed` is initialised, tracks are block-partitioned by global id over the ranks, fields are
 replicated, the potential solve is row-sharded and presence maps are summed with one all-reduce (NCCL on GPUs).
     case_parallel=True   instead distributes the wind CASES over the ranks (seasonal mode: rank r takes cases
@@ -45,7 +50,8 @@ from . import dist as _dist
 from . import trackio
 from .config import Config
 from .layers import get_above_threshold_speed, updraft_fields
-from .movmodel import MovModel, get_starting_indices, interleave_fields, simulate_tracks_batch
+from .movmodel import (MovModel, get_starting_indices, interleave_fields, record_tracks_packed,
+                       simulate_tracks_batch)
 from .potential import solve_potential_device
 
 TRACKS_PKL_LIMIT = 50_000      # above this the pickled list-of-arrays format is impractical; a packed .npz is written
@@ -108,7 +114,8 @@ class Simulator(Config):
     time_format = 'y%Ym%md%dh%H'
 
     def __init__(self, in_config: Config = None, *, elevation=None, wind_cases: Optional[Dict] = None,
-                 wind_points=None, bounds=None, case_parallel: bool = False, **kwargs) -> None:
+                 wind_points=None, bounds=None, case_parallel: bool = False, force_potential: bool = False,
+                 **kwargs) -> None:
         if in_config is None:
             super().__init__(**kwargs)
         else:
@@ -159,6 +166,7 @@ class Simulator(Config):
             raise ValueError(f"elevation shape {tuple(z.shape)} does not match gridsize {self.gridsize}")
         self._elev = z
         self._writer = _ArtefactWriter()
+        self._force_potential = bool(force_potential)
         self._oro_cache: Dict[str, "torch.Tensor"] = {}       # float32 orographs kept on the device (what the .npy holds)
         self._presence: Dict[str, "torch.Tensor"] = {}
         self._track_results = {}
@@ -172,6 +180,11 @@ class Simulator(Config):
             self._wind_cases = wind_cases
             self._wind_points = None
             if wind_points is not None:
+                if self.wtk_interp_type not in ('linear', 'nearest'):
+                    # documented rejection: griddata's 'cubic' (Clough-Tocher) is not built; failing in
+                    # the constructor beats failing after the terrain work
+                    raise ValueError(f"wtk_interp_type={self.wtk_interp_type!r} is not supported by ssrs_b200: "
+                                     f"use 'linear' (the reference's default, config.py:44) or 'nearest'")
                 from .layers import delaunay_triangles
                 xl, yl = (np.asarray(v, dtype=np.float64) for v in wind_points)
                 self._wind_points = (xl, yl, delaunay_triangles(xl, yl))       # one triangulation for all cases
@@ -299,14 +312,35 @@ class Simulator(Config):
         return os.path.join(dirname, f'{case_id}_r{real_id}_thermals')
 
     # ---------------------------------------------------------------- stage 2
+    def _potential_key(self, updraft) -> str:
+        """Content key of a potential: what the solve consumes (thresholded updraft raster, direction, grid)."""
+        import hashlib
+        torch = N.require_cuda()
+        u = updraft if isinstance(updraft, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(updraft, dtype=np.float32))
+        u = u.to(device="cuda", dtype=torch.float32).contiguous()
+        # two independent 64-bit sums of the raster's bit patterns, computed on the device (a 120 MB raster would take
+        # longer to hash on the host than to solve)
+        bits = u.view(torch.int32).to(torch.int64).ravel()
+        idx = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64)
+        s1 = int(bits.sum().item()) & (2 ** 64 - 1)
+        s2 = int((bits * (idx % 1000003 + 1)).sum().item()) & (2 ** 64 - 1)
+        raw = f"{self.gridsize}|{float(self.track_direction)!r}|{s1:x}|{s2:x}"
+        return hashlib.sha256(raw.encode()).hexdigest()[:32]
+
     def get_directional_potential(self, updraft, case_id, real_id):
         """float32 potential for (case, realisation); cached as `<id>_potential.npy` like the reference
-        (:259-288, including its cache rules).  `updraft` may be numpy or a CUDA tensor."""
+        (:259-288, including its cache rules) plus a content key (see the class docstring).  `updraft` may be numpy or
+        a CUDA tensor.  An unconverged solve raises and is never cached."""
         torch = N.require_cuda()
         fname = self._get_potential_fname(case_id, real_id, self.mode_data_dir)
         id_str = self._get_id_string(case_id, real_id)
+        key = self._potential_key(updraft)
         try:
-            if not self._d.agree(os.path.exists(f'{fname}.npy')):
+            usable = (not self._force_potential) and os.path.exists(f'{fname}.npy') and os.path.exists(f'{fname}.key')
+            if usable:
+                with open(f'{fname}.key') as f:
+                    usable = f.read().strip() == key
+            if not self._d.agree(usable):
                 raise FileNotFoundError         # the solve is collective: all ranks follow rank 0's view of the cache
             potential = np.load(f'{fname}.npy')
             if potential.shape != self.gridsize:
@@ -323,13 +357,23 @@ class Simulator(Config):
             self.timings['potential_s'] = time.time() - t0
             self.solve_stats = stats
             print(f'took {_elapsed(t0)}', flush=True)
+            if not stats['converged']:
+                # the reference's direct solve cannot fail this way; a wrong field must neither be stepped on nor cached
+                raise N.NativeError(f"{id_str}: potential solve did not converge (relative residual "
+                                    f"{stats['rel_residual']:.3e} after {stats['iterations']} iterations); nothing was cached")
             potential = pot_dev.cpu().numpy()
             if self._d.rank() == 0:
-                self._writer.submit(np.save, f'{fname}.npy', potential)
+                self._writer.submit(self._save_potential, fname, potential, key)
         if np.isnan(potential).any():
             print('NANs found in potential!')
         self._last_potential_device = pot_dev
         return potential
+
+    @staticmethod
+    def _save_potential(fname, potential, key):
+        np.save(f'{fname}.npy', potential)
+        with open(f'{fname}.key', 'w') as f:       # written after the raster: a key without a complete raster cannot exist
+            f.write(key + '\n')
 
     def _get_id_string(self, case_id: str, real_id: Optional[int] = None):
         out = f'{case_id}_d{int(self.track_direction % 360)}_t{int(self.updraft_threshold * 100)}_{self.movement_model}'
@@ -373,8 +417,7 @@ class Simulator(Config):
                 t0 = time.time()
                 res = simulate_tracks_batch(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
                                             self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
-                                            fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
-                                            record=record)
+                                            fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo)
                 presence = self._d.presence_allreduce(res.presence)        # ssrs_presence_allreduce (NCCL) when world > 1
                 steps = self._d.allreduce_sum(res._total.clone())
                 torch.cuda.synchronize()
@@ -383,18 +426,25 @@ class Simulator(Config):
                 print(f'took {_elapsed(t0)}', flush=True)
                 self._presence[id_str] = presence
                 fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
-                if record and n <= TRACKS_PKL_LIMIT:
-                    tracks = res.tracks()
-                    tracks = self._d.gather_tracks(tracks)
-                    if self._d.rank() == 0:
-                        self._writer.submit(trackio.save_tracks_pickle, fname, tracks)        # the reference's file (:383-386)
-                elif record:
-                    # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
-                    off, pts = res.packed()
-                    suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
-                    self._writer.submit(trackio.save_tracks_packed, f'{fname}{suffix}', off, pts)
-                if not record and self._d.rank() == 0:
-                    # (uncompressed: compressing a 120 MB raster costs seconds)
+                if record:
+                    # trajectories: a second, recording pass in chunks sized by the now known lengths (the longest track
+                    # is ~10x the mean, so one dense [longest, n] buffer would be mostly padding); the counter-based
+                    # streams make it repeat the counting pass step for step
+                    off, pts = record_tracks_packed(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
+                                                    self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
+                                                    fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
+                                                    lengths=res.traj_len.cpu().numpy())
+                    if n <= TRACKS_PKL_LIMIT:
+                        tracks = self._d.gather_tracks([a.copy() for a in trackio.unpack_tracks(off, pts)])
+                        if self._d.rank() == 0:
+                            self._writer.submit(trackio.save_tracks_pickle, fname, tracks)    # the reference's file (:383-386)
+                    else:
+                        # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
+                        suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
+                        self._writer.submit(trackio.save_tracks_packed, f'{fname}{suffix}', off, pts)
+                if self._d.rank() == 0:
+                    # counts of every run are kept on disk (uncompressed: compressing a 120 MB raster costs seconds), so
+                    # that a fresh Simulator over this run directory can build the presence map without the tracks
                     self._writer.submit(np.savez, f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
         self.flush()
 
@@ -404,14 +454,32 @@ class Simulator(Config):
         case_id = self.case_ids[0] if case_id is None else case_id
         return trackio.load_tracks(self._get_tracks_fname(case_id, real_id, self.mode_data_dir))
 
-    def presence_counts(self, case_id: Optional[str] = None, real_id: int = 0) -> np.ndarray:
-        """int32 visit counts of the last simulate_tracks() (reference compute_presence_counts, movmodel.py:410-419)."""
-        case_id = self.case_ids[0] if case_id is None else case_id
+    def _presence_device(self, case_id: str, real_id: int):
+        """Counts of (case, realisation) on the device: from this object's last simulate_tracks(), else from the run
+        directory (`<id>_tracks_presence_counts.npz`, or recounted from the stored tracks like the reference, which
+        re-reads `<id>_tracks.pkl`, simulator.py:525-529)."""
+        torch = N.require_cuda()
         key = self._get_id_string(case_id, real_id)
         if key not in self._presence:
-            raise KeyError(f"no presence counts for {key} on this rank (not simulated yet, or owned by another rank "
-                           f"in case_parallel mode)")
-        return self._presence[key].cpu().numpy()
+            fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
+            if os.path.exists(f'{fname}_presence_counts.npz'):
+                with np.load(f'{fname}_presence_counts.npz') as z:
+                    counts = z['counts']
+            else:
+                try:
+                    tracks = trackio.load_tracks(fname)
+                except FileNotFoundError:
+                    raise KeyError(f"no presence counts for {key}: not simulated by this Simulator and neither "
+                                   f"{fname}_presence_counts.npz nor stored tracks exist in the run directory") from None
+                from .movmodel import compute_presence_counts
+                counts = compute_presence_counts(tracks, self.gridsize)
+            self._presence[key] = torch.from_numpy(np.ascontiguousarray(counts, dtype=np.int32)).to("cuda")
+        return self._presence[key]
+
+    def presence_counts(self, case_id: Optional[str] = None, real_id: int = 0) -> np.ndarray:
+        """int32 visit counts of (case, realisation) (reference compute_presence_counts, movmodel.py:410-419)."""
+        case_id = self.case_ids[0] if case_id is None else case_id
+        return self._presence_device(case_id, real_id).cpu().numpy()
 
     def _get_tracks_fname(self, case_id: str, real_id: int, dirname: str):
         return os.path.join(dirname, f'{self._get_id_string(case_id, real_id)}_tracks')
@@ -428,7 +496,7 @@ class Simulator(Config):
         for case_id in self._my_case_ids():
             case_prob = None
             for real_id in range(1 + int(self.thermals_realization_count)):
-                counts = self._presence[self._get_id_string(case_id, real_id)]
+                counts = self._presence_device(case_id, real_id)
                 pr = smooth_presence_counts(counts, int(round(krad)))
                 pr = pr / pr.max()
                 case_prob = pr if case_prob is None else case_prob + pr

@@ -6,7 +6,9 @@ content), but a million pickled arrays are impractical, so large runs use a pack
 
     <id>_tracks.npz :  offsets int64 [n_tracks + 1],  points int16 [offsets[-1], 2]   (row, col)
 
-track t is `points[offsets[t]:offsets[t + 1]]`.  `load_tracks` reads either and returns the reference's list.
+track t is `points[offsets[t]:offsets[t + 1]]`.  A multi-rank run writes one packed file per rank,
+`<id>_tracks_part<r>of<w>.npz`, holding that rank's contiguous block of global track ids.  `load_tracks` reads any of
+the three and returns the reference's list (parts concatenated in rank order).
 """
 from __future__ import annotations
 
@@ -64,4 +66,33 @@ def load_tracks(fname: str) -> List[np.ndarray]:
     if os.path.exists(f"{base}.npz"):
         with np.load(f"{base}.npz") as z:
             return unpack_tracks(z["offsets"], z["points"])
-    raise FileNotFoundError(f"no track file {base}.pkl or {base}.npz")
+    parts = part_files(base)
+    if parts:
+        out: List[np.ndarray] = []
+        for path in parts:                          # rank order = global track-id order (block partition, dist.py)
+            with np.load(path) as z:
+                out.extend(unpack_tracks(z["offsets"], z["points"]))
+        return out
+    raise FileNotFoundError(f"no track file {base}.pkl, {base}.npz or {base}_part*of*.npz")
+
+
+def part_files(base: str) -> List[str]:
+    """The `<base>_part<r>of<w>.npz` files a multi-rank run writes (one per rank, Simulator.simulate_tracks), in rank
+    order.  Raises if the set is incomplete or mixes world sizes; [] if there is none."""
+    import glob
+    import re
+    found = {}
+    for path in glob.glob(f"{glob.escape(base)}_part*of*.npz"):
+        m = re.fullmatch(r"_part(\d+)of(\d+)\.npz", path[len(base):])
+        if m:
+            found[(int(m.group(1)), int(m.group(2)))] = path
+    if not found:
+        return []
+    worlds = {w for _, w in found}
+    if len(worlds) != 1:
+        raise ValueError(f"track parts of different runs under {base}_part*: world sizes {sorted(worlds)}")
+    world = worlds.pop()
+    missing = [r for r in range(world) if (r, world) not in found]
+    if missing:
+        raise FileNotFoundError(f"track parts {missing} of {world} are missing under {base}_part*")
+    return [found[(r, world)] for r in range(world)]

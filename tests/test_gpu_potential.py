@@ -43,6 +43,26 @@ def test_oracle_500x600():
     assert (phi.cpu().numpy() != ref.astype(np.float32)).mean() < 0.25      # the direct solve itself is only good to ~1 ulp
 
 
+def test_refined_truth_10m(golden):
+    """10 m resolution (all large configs): the GPU potential vs the refined truth of the reference's linear system at
+    1000 x 1200 (SuperLU + long-double refinement, oracle/make_golden_truth10m.py) — within 2 float32 ulp, measured
+    both against ulp(1000) and against every cell's own ulp.  (The reference's unrefined SuperLU float32 potential is
+    14 ulp off the same truth; stored in the fixture.)"""
+    from ssrs_b200.potential import solve_potential_device
+    g = golden("potential_truth10m")
+    K, truth = g["K32"], g["phi_truth32"]
+    phi, stats = solve_potential_device(K, 0.0)
+    phi = phi.cpu().numpy()
+    assert stats["converged"] in (1, 2)
+    d = np.abs(phi.astype(np.float64) - truth.astype(np.float64))
+    local = d / np.spacing(np.abs(truth)).astype(np.float64).clip(1e-300)
+    print(f"10 m truth: max error {d.max() / ULP:.2f} ulp(1000), {local.max():.2f} local ulp, "
+          f"{100 * (phi != truth).mean():.2f} % of cells differ; reference SuperLU: "
+          f"{np.abs(g['superlu_minus_truth_ulp']).max()} ulp; {stats['iterations']} iterations")
+    assert d.max() <= 2 * ULP and local.max() <= 2.0
+    assert d.max() <= CONTRACT
+
+
 def test_full_size_residual_and_bounds():
     """(5000, 6000) at 10 m: no reference solve exists at this size.  Checked with the
     oracle's operator: scaled residual of the float64-widened float32 potential at free nodes is at

@@ -47,3 +47,21 @@ def test_bad_arguments():
     assert rc == -1
     rc, *_ = hostemu.solve(K, np.array([1000]), np.array([0.0]))
     assert rc == -1
+
+
+def test_refined_truth_10m(golden):
+    """1000 x 1200 cells at 10 m — the resolution of every large BASELINE config — against the refined truth
+    (tests/golden/potential_truth10m.npz, oracle/make_golden_truth10m.py: SuperLU + long-double iterative refinement of
+    the reference's own linear system).  The reference's unrefined SuperLU answer is itself 14 float32 ulp off that
+    truth, so it cannot serve as the yardstick here; the solver must be within 2 ulp of the truth."""
+    g = golden("potential_truth10m")
+    K, truth = g["K32"], g["phi_truth32"]
+    assert np.abs(g["superlu_minus_truth_ulp"]).max() >= 10          # why the truth fixture exists
+    bn, bv = O.boundary_nodes(0.0, *K.shape)
+    rc, phi, st, err = hostemu.solve(K, bn, bv)
+    assert rc == 0 and st.converged in (1, 2), err
+    d = np.abs(phi.astype(np.float64) - truth.astype(np.float64))
+    assert d.max() <= 2 * ULP, d.max() / ULP
+    local = d / np.spacing(np.abs(truth)).astype(np.float64).clip(1e-300)
+    assert local.max() <= 2.0, local.max()                           # in ulps of each cell's own value
+    assert (phi != truth).mean() < 0.1

@@ -53,3 +53,20 @@ def test_packed_from_device_matches_list():
     lst = res.tracks()
     back = trackio.unpack_tracks(off, pts)
     assert len(back) == n and all(np.array_equal(a, b) for a, b in zip(back, lst))
+
+
+def test_multi_rank_parts(tmp_path):
+    """`<id>_tracks_part<r>of<w>.npz` written by the ranks of a sharded run load as one list in global-id order."""
+    rng = np.random.RandomState(3)
+    tracks = _tracks(rng, 41)
+    base = str(tmp_path / "c_tracks")
+    bounds = [0, 14, 28, 41]
+    for r in range(3):
+        off, pts = trackio.pack_tracks(tracks[bounds[r]:bounds[r + 1]])
+        trackio.save_tracks_packed(f"{base}_part{r}of3", off, pts)
+    got = trackio.load_tracks(base)
+    assert len(got) == 41 and all(np.array_equal(a, b) for a, b in zip(got, tracks))
+    import os
+    os.remove(f"{base}_part1of3.npz")
+    with pytest.raises(FileNotFoundError):
+        trackio.load_tracks(base)
