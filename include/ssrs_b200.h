@@ -65,6 +65,13 @@ SSRS_API int ssrs_updraft(const float* dem, int rows, int cols, float resolution
                  float* slope_deg, float* aspect_deg, float* orograph, float* updraft,
                  void* stream);
 
+/* compute_orographic_updraft alone (ssrs/layers.py:11-22) on slope / aspect rasters in degrees — the reference's
+ * signature for callers that hold those rasters (3DEP 'Slope' / 'Aspect' layers, ssrs/simulator.py:152-168);
+ * wspeed / wdirn: per-cell rasters or NULL for the uniform values.  out = max(V sin(slope) max(cos(aspect - dirn), 0), min_updraft). */
+SSRS_API int ssrs_orographic_updraft(const float* slope_deg, const float* aspect_deg, const float* wspeed, const float* wdirn,
+                            float uniform_wspeed, float uniform_wdirn_deg, float min_updraft, float* out, int64_t n,
+                            void* stream);
+
 /* get_above_threshold_speed alone (ssrs/layers.py:171-185) for rasters that did not come from
  * ssrs_updraft (e.g. orograph + thermals, ssrs/simulator.py:236-242). */
 SSRS_API int ssrs_threshold(const float* in, float* out, int64_t n, float threshold, void* stream);
@@ -103,6 +110,14 @@ SSRS_API int ssrs_potential_solve(const float* conductivity, int rows, int cols,
 
 /* Frees the solver's cached workspace on the current device (not while a solve is running). */
 SSRS_API int ssrs_release_workspace(void);
+
+/* ssrs_potential_solve that also returns the float64 iterate the float32 potential was rounded from (potential64:
+ * float64 [rows][cols]) — for diagnostics: the reference's tracks are steered by float32 rounding plateaus of the
+ * potential (SURVEY.md §0 finding 4), so tests check the discrete maximum principle on the un-rounded solution. */
+SSRS_API int ssrs_potential_solve_f64(const float* conductivity, int rows, int cols,
+                             const int64_t* bnodes_host, const double* bvalues_host, int64_t n_bnodes,
+                             double rtol, int max_iter, float* potential, double* potential64,
+                             ssrs_solve_stats* stats, void* stream);
 
 /* Row-sharded solve (BASELINE config 5): the grid's rows are split into `comm->size` contiguous
  * slabs; rank r owns slab r.  Every rank passes the SAME full conductivity raster (fields are replicated for the
@@ -176,9 +191,9 @@ SSRS_API int ssrs_presence_allreduce(uint32_t* presence, int64_t n, const ssrs_c
  *         trajectory points (= steps + 1).   presence (optional): uint32 [rows][cols], incremented
  *         atomically (not cleared).   total_steps (optional): one uint64, incremented by the number
  *         of track-steps taken (loop iterations at ssrs/movmodel.py:285-317).
- * Asynchronous on `stream`.  Tracks beyond the first per resident thread are handed out through a device counter
- * (8 bytes per launch, taken from an 8 KB per-device array the library allocates on first use and zeroes on
- * `stream`): which lane steps which track varies from run to run, the results do not (see above).
+ * Asynchronous on `stream`.  Tracks are handed to the lanes through a device counter (8 bytes per launch, taken
+ * from an 8 KB per-device array the library allocates on first use and zeroes on `stream`): which lane steps which
+ * track varies from run to run, the results do not (see above).
  */
 #define SSRS_STEP_EXACT 1
 
@@ -190,6 +205,54 @@ SSRS_API int ssrs_step_tracks(const float* fields, int rows, int cols,
                      uint32_t* presence, unsigned long long* total_steps,
                      int flags, void* stream);
 
+/* ssrs_step_tracks as a PHASED launch (track_dirn_restrict = 1; other values run as one launch): track lengths are
+ * heavy-tailed — at 5000 x 6000 the median track takes 9e3 steps, 1 % take more than 3e4 and the longest 1.2e5 — so a
+ * launch that steps every track to its end runs most of its life with a few lanes per warp alive.  Here the stepping
+ * is cut at fixed step counts (first cut after about one crossing of the grid's short side, then x1.25; or
+ * first_phase_steps > 0): each phase's kernel appends the survivors' states (16 bytes) to a compact list, the next
+ * phase's kernel packs them into full warps again and its surplus CTAs exit at once, which frees SMs for other
+ * streams' launches.  Same arguments and bit-identical results as ssrs_step_tracks (the random stream is keyed by
+ * track id and step); workspace = ssrs_walk_workspace_bytes(n_tracks) bytes, caller-owned, reusable once `stream`
+ * has passed the call. */
+SSRS_API int ssrs_step_tracks_phased(const float* fields, int rows, int cols,
+                     const int32_t* start_rc, int64_t n_tracks, int64_t track_id0,
+                     const double* dirprob9_host, int memory, double nu,
+                     uint64_t seed, const double* uniforms, int64_t uniforms_stride,
+                     int16_t* traj, int64_t traj_cap, int32_t* traj_len,
+                     uint32_t* presence, unsigned long long* total_steps,
+                     int flags, void* workspace, int64_t workspace_bytes, int first_phase_steps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3+4 for large batches — transition-table walk (ssrs_b200/csrc/walk.cu).  Same reference functions as
+ * ssrs_step_tracks (generate_simulated_tracks ssrs/movmodel.py:264-318 mapped over the pool at
+ * ssrs/simulator.py:360-369; compute_presence_counts ssrs/movmodel.py:410-419), for the default movement settings
+ * track_dirn_restrict = 1 and track_stochastic_nu = 1 (ssrs/config.py:56-57), where the move distribution of
+ * movmodel.py:294-312 depends on the cell and the previous move only:
+ *   ssrs_transition_table  evaluates it once per (cell, previous move) from the interleaved fields — production
+ *                          arithmetic of ssrs_step_tracks, fallback chain of movmodel.py:228-240 included — as two 31-bit
+ *                          cumulative thresholds; table = ssrs_walk_table_bytes(rows, cols) = 64 bytes per cell;
+ *   ssrs_walk_tracks       steps every track with one 8-byte gather, two integer compares on a Philox word and one
+ *                          presence increment per step.  Cells within two rows / one column of the border, a track's
+ *                          first steps and steps near its step limit take ssrs_step_tracks' general step on `fields`.
+ *                          The walk is cut into phases at fixed step counts; survivors are compacted between phases
+ *                          (workspace = ssrs_walk_workspace_bytes(n_tracks), caller-owned, reusable once the stream
+ *                          has passed the call).  first_phase_steps: 0 = default schedule (first cut after about one
+ *                          crossing of the grid's short side, then x1.25), else the first cut (tests).
+ * Random numbers: Philox4x32-10 keyed by seed with counter (track_id0 + t, step): results do not depend on sharding or
+ * on the phase schedule.  The mapping of words to steps differs from ssrs_step_tracks (documented in walk.cu and
+ * restated by oracle/ssrs_oracle.c), so the two entry points give different realisations of the same distribution;
+ * probabilities are quantised to 2^-31.  traj_len, total_steps optional; presence required (uint32, not cleared).
+ * Asynchronous on `stream`. */
+SSRS_API int64_t ssrs_walk_table_bytes(int rows, int cols);
+SSRS_API int64_t ssrs_walk_workspace_bytes(int64_t n_tracks);
+SSRS_API int ssrs_transition_table(const float* fields, int rows, int cols, const double* dirprob9_host, void* table,
+                          void* stream);
+SSRS_API int ssrs_walk_tracks(const void* table, const float* fields, int rows, int cols,
+                     const int32_t* start_rc, int64_t n_tracks, int64_t track_id0,
+                     const double* dirprob9_host, uint64_t seed,
+                     int32_t* traj_len, uint32_t* presence, unsigned long long* total_steps,
+                     void* workspace, int64_t workspace_bytes, int first_phase_steps, void* stream);
+
 /* {updraft, potential} -> interleaved pairs (one 8-byte gather per cell in the stepping kernel). */
 SSRS_API int ssrs_interleave_fields(const float* updraft, const float* potential, float* fields,
                            int64_t n, void* stream);
@@ -198,6 +261,10 @@ SSRS_API int ssrs_interleave_fields(const float* updraft, const float* potential
  * traj int16 [traj_cap][n_tracks][2] step-major + traj_len as written by ssrs_step_tracks. */
 SSRS_API int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len,
                          int64_t n_tracks, int rows, int cols, uint32_t* presence, void* stream);
+
+/* Running sums of a uint32 count raster along each row, the input of ssrs_smooth_presence:
+ * row_prefix int64 [rows][cols+1], row_prefix[r][0] = 0, row_prefix[r][c+1] = counts[r][0] + ... + counts[r][c]. */
+SSRS_API int ssrs_row_prefix_sums(const uint32_t* counts, int rows, int cols, long long* row_prefix, void* stream);
 
 /* compute_smooth_presence_counts (ssrs/movmodel.py:422-439): disk kernel of `radius` cells, zero padding
  * ('same'), normalised by the kernel's cell count.  row_prefix: int64 [rows][cols+1] running sums of the

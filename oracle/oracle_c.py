@@ -59,8 +59,18 @@ def step_tracks(U, P, shape, start_rc, move_dirn, memory=1, nu=1.0, seed=0, trac
     presence = np.zeros((rows, cols), dtype=np.int32) if want_presence else None
     total = lib().oracle_step_tracks(_ptr(U), _ptr(P), rows, cols, _ptr(start_rc), n, track_id0, _ptr(dirp),
                                      int(memory), float(nu), int(seed), _ptr(uniforms), ustride, _ptr(traj),
-                                     traj_cap, _ptr(traj_len), _ptr(presence), int(nthreads), int(bool(fast)))
+                                     traj_cap, _ptr(traj_len), _ptr(presence), int(nthreads), _mode(fast, U, memory, nu, uniforms, traj_cap))
     return dict(total_steps=int(total), traj_len=traj_len, traj=traj, presence=presence)
+
+
+def _mode(fast, U, memory, nu, uniforms, traj_cap):
+    """0: the reference's exact operation order; 1 (fast=True): production arithmetic of tracks.cu; 2 (fast='table'): the
+    transition-table walk of walk.cu (needs fields, memory 1, nu 1, Philox streams, no trajectories)."""
+    if fast == "table":
+        if U is None or memory != 1 or nu != 1.0 or uniforms is not None or traj_cap:
+            raise ValueError("table mode needs fields, memory 1, nu 1, Philox streams and no trajectory output")
+        return 2
+    return int(bool(fast))
 
 
 def presence_counts(traj, traj_len, shape):

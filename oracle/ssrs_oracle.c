@@ -251,6 +251,120 @@ static int64_t one_track(const float* U, const float* P, int nr, int nc, int row
     return k + 1;
 }
 
+/* ---- "table" mode: the transition-table walk of ssrs_b200/csrc/walk.cu, restated step for step ----------------------
+ * With direction memory 1 and nu = 1 the move distribution is a function of (cell, previous move).  walk.cu tabulates
+ * it once per (case, realisation) as two cumulative thresholds on the 2^-31 lattice and steps with one 31-bit Philox
+ * word per move; here the same thresholds are evaluated on demand.  Step types and random-number mapping as documented
+ * at the top of walk.cu. */
+static const uint32_t W_ONE = 0x80000000u, W_UNMASKED = 0xFFFFFFFFu;
+
+static uint32_t prob31(double p) {
+    const double x = p * 2147483648.0 + 0.5;
+    return x >= 2147483648.0 ? W_ONE : (uint32_t)x;
+}
+
+static double clip_updraft(float x) { return (x > 9.99999997475242707e-07f) ? (double)x : 1e-06; }
+
+static void table_entry(const float* U, const float* P, int nc, int r, int c, int last, const double* dirp,
+                        uint32_t* t1, uint32_t* t2) {
+    const float ninv_d = 0.70710677f;
+    const int* ci = CAND3[last];
+    const int64_t o = (int64_t)r * nc + c;
+    const double uc = clip_updraft(U[o]);
+    double dq[3], ss[3];
+    for (int j = 0; j < 3; ++j) {
+        const int dr = ci[j] / 3 - 1, dc = ci[j] % 3 - 1;
+        const int64_t qn = o + (int64_t)dr * nc + dc;
+        const float ninv = (dr != 0 && dc != 0) ? ninv_d : 1.0f;
+        const float d = (float)(P[o] - P[qn]) * ninv;
+        const float dm = (d != d) ? d : (d > 0.0f ? d : 0.0f);                 /* max.NaN(d, 0) */
+        const double u = clip_updraft(U[qn]);
+        dq[j] = (double)dm * u;
+        ss[j] = uc + u;
+    }
+    double q0 = dq[0] * (ss[1] * ss[2]), q1 = dq[1] * (ss[0] * ss[2]), q2 = dq[2] * (ss[0] * ss[1]);
+    double c1 = q0 + q1, c2 = c1 + q2;
+    if (!(c2 > 0.0 && c2 <= 1.7976931348623157e308)) {
+        q0 = dirp[ci[0]]; q1 = dirp[ci[1]]; q2 = dirp[ci[2]];
+        c1 = q0 + q1; c2 = c1 + q2;
+        if (!(c2 > 0.0)) { *t1 = W_UNMASKED; *t2 = 0; return; }
+    }
+    const double inv = 1.0 / c2;
+    uint32_t a = (q0 > 0.0) ? prob31(q0 * inv) : 0u;
+    uint32_t b = (q2 > 0.0) ? prob31(c1 * inv) : W_ONE;
+    if (!(q1 > 0.0) && !(q2 > 0.0)) a = W_ONE;
+    if (b < a) b = a;
+    *t1 = a; *t2 = b;
+}
+
+static int64_t one_track_table(const float* U, const float* P, int nr, int nc, int row, int col, const double* dirp,
+                               uint64_t seed, uint64_t gid, int32_t* presence) {
+    const int burnin = (int)((nr < nc ? nr : nc) / 10);
+    const double max_moves = (double)nr / 2 * (double)nc / 2;
+    const double km = ceil(max_moves);
+    const int64_t kmax = km > 2147483647.0 ? 2147483647 : (int64_t)km;
+    uint32_t dthr[9];
+    {
+        double run[9], acc = 0.0;
+        int lastpos = -1;
+        for (int i = 0; i < 9; ++i) { acc += dirp[i]; run[i] = acc; if (dirp[i] > 0.0) lastpos = i; }
+        for (int i = 0; i < 9; ++i) {
+            const double x = run[i] / run[8] * 2147483648.0 + 0.5;
+            dthr[i] = (i >= lastpos || x >= 2147483648.0) ? W_ONE : (uint32_t)x;
+        }
+    }
+    int64_t k = 0;
+    int last = 4, tmode = 0;
+    if (presence) {
+#pragma omp atomic
+        presence[(int64_t)row * nc + col] += 1;
+    }
+    for (;;) {
+        const int elig = last != 4 && row >= 2 && row <= nr - 3 && col >= 1 && col <= nc - 3;
+        if ((k & 3) == 0) tmode = elig && k + 4 <= kmax;
+        else tmode = tmode && elig;
+        int idx;
+        if (tmode) {
+            uint32_t w[4], t1, t2;
+            philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(k >> 2), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+            const uint32_t r31 = w[k & 3] >> 1;
+            table_entry(U, P, nc, row, col, last, dirp, &t1, &t2);
+            if (t1 == W_UNMASKED) {
+                int cnt = 0;
+                for (int i = 0; i < 9; ++i) cnt += (r31 >= dthr[i]) ? 1 : 0;
+                idx = cnt < 8 ? cnt : 8;
+            } else idx = CAND3[last][(r31 < t1) ? 0 : ((r31 < t2) ? 1 : 2)];
+            row += idx / 3 - 1;
+            col += idx % 3 - 1;
+        } else {
+            if (k >= kmax) break;                                              /* movmodel.py:285 */
+            int r = row, c = col;
+            if (k > burnin) {
+                if (!(0 < r && r < nr - 1 && 0 < c && c < nc - 1)) break;
+            } else {
+                if (r <= 1) r += 2; else if (r >= nr - 2) r -= 2;
+                if (c <= 0) c += 2; else if (c >= nc - 2) c -= 2;
+            }
+            uint32_t w[4];
+            philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)k, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+            const uint64_t bits = 0x3FF0000000000000ULL | ((uint64_t)w[0] << 20) | (uint64_t)(w[1] >> 12);
+            double u;
+            memcpy(&u, &bits, 8);
+            u -= 1.0;
+            idx = choose_fast(U, P, nc, r, c, dirp, RESTRICT_LUT[last], 1.0, u, last);
+            row = r + (idx / 3 - 1);
+            col = c + (idx % 3 - 1);
+        }
+        ++k;
+        last = idx;
+        if (presence) {
+#pragma omp atomic
+            presence[(int64_t)row * nc + col] += 1;
+        }
+    }
+    return k + 1;
+}
+
 /* Batch driver.  start_rc int32 [n][2]; uniforms [n][ustride] or NULL; traj int16 [n][cap][2] track-major
  * or NULL; traj_len int32 [n] or NULL; presence int32 [rows][cols] or NULL.  Returns total track-steps. */
 int64_t oracle_step_tracks(const float* U, const float* P, int rows, int cols, const int32_t* start_rc, int64_t n,
@@ -263,9 +377,14 @@ int64_t oracle_step_tracks(const float* U, const float* P, int rows, int cols, c
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : total) num_threads(nthreads)
 #endif
     for (int64_t t = 0; t < n; ++t) {
-        int64_t len = one_track(U, P, rows, cols, start_rc[2 * t], start_rc[2 * t + 1], dirp, memory, nu, seed,
-                                (uint64_t)(track_id0 + t), uniforms ? uniforms + t * ustride : NULL,
-                                traj ? traj + t * cap * 2 : NULL, cap, presence, fast);
+        int64_t len;
+        if (fast == 2)      /* transition-table walk (memory 1, nu 1, Philox, fields given, no trajectories) */
+            len = one_track_table(U, P, rows, cols, start_rc[2 * t], start_rc[2 * t + 1], dirp, seed,
+                                  (uint64_t)(track_id0 + t), presence);
+        else
+            len = one_track(U, P, rows, cols, start_rc[2 * t], start_rc[2 * t + 1], dirp, memory, nu, seed,
+                            (uint64_t)(track_id0 + t), uniforms ? uniforms + t * ustride : NULL,
+                            traj ? traj + t * cap * 2 : NULL, cap, presence, fast);
         if (traj_len) traj_len[t] = (int32_t)len;
         total += len - 1;
     }

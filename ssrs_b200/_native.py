@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssrs_b200.so")
+LIB_PATH = os.environ.get("SSRS_B200_LIB") or os.path.join(_HERE, "libssrs_b200.so")    # override: kernel A/B experiments
 
 EXPORTS = {
     # name: (restype, argtypes)
@@ -18,9 +18,13 @@ EXPORTS = {
     "ssrs_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "ssrs_updraft": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_orographic_updraft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_int64, C.c_void_p]),
     "ssrs_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "ssrs_potential_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int64,
                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_potential_solve_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int64,
+                                           C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_potential_solve_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                                C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_interp_wind": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
@@ -38,7 +42,18 @@ EXPORTS = {
     "ssrs_step_tracks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                    C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ssrs_walk_table_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "ssrs_walk_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "ssrs_transition_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
+    "ssrs_walk_tracks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.POINTER(C.c_double), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_int, C.c_void_p]),
+    "ssrs_step_tracks_phased": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                          C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ssrs_interleave_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ssrs_row_prefix_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ssrs_smooth_presence": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ssrs_presence_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p]),

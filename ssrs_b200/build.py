@@ -19,8 +19,8 @@ LIB = os.path.join(HERE, "libssrs_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "-Xptxas", "-v", "-cudart", "shared"]
-# per-file extra flags: the stepping kernel must not contract a*b+c (bit-exact float64 parity with numpy)
-EXTRA = {"tracks.cu": ["-fmad=false"]}
+# per-file extra flags: the stepping kernels must not contract a*b+c (bit-exact float64 parity with numpy)
+EXTRA = {"tracks.cu": ["-fmad=false"], "walk.cu": ["-fmad=false"]}
 
 
 def nvcc() -> str:

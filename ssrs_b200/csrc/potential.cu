@@ -1056,7 +1056,7 @@ extern "C" __attribute__((visibility("default"))) const char* ssrs_emu_last_erro
 namespace ssrs { namespace amg {
 int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, const double* bvalues_host,
                int64_t n_bnodes, double rtol, int max_iter, float* phi, ssrs_solve_stats* stats, const ssrs_comm* comm,
-               void* stream) {
+               void* stream, double* phi64 = nullptr) {
     if (comm != nullptr && comm->size <= 1) comm = nullptr;
     if (comm != nullptr) {
         if (comm->size > SSRS_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->size || !comm->exchange || !comm->allreduce_sum || !comm->allgather) {
@@ -1273,19 +1273,22 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     // Attainable accuracy: the nearest float64-representable potential leaves a residual of about
     // d_i * ulp(phi_i) / 2 per cell (d_i = row diagonal); below that the recurrence residual keeps falling but
     // the true one does not (the estimate is 1.5-4x above the floor measured on 300 k .. 30 M cell grids).  The
-    // recurrence residual is iterated to the larger of rtol and floor/2, then the true residual decides: accepted
-    // below floor/2, else the iteration restarts from the current iterate (typically one more iteration).
+    // recurrence residual is iterated to the larger of rtol and a fraction of that floor, then the true residual decides:
+    // accepted below the same fraction (or when it has stagnated), else the iteration restarts from the current iterate.
     double floor2 = 0.0, bmax = 0.0;
     for (int64_t q = 0; q < n_bnodes; ++q) bmax = fabs(bvalues_host[q]) > bmax ? fabs(bvalues_host[q]) : bmax;
     { const float* dinv = H.f32.dinv; const double scale = 0.5 * 2.220446049250313e-16 * bmax;
       AMG_TRY(preduce_sum(n, st, &floor2, [=] SSRS_HD(i64 i) { const double di = (double)dinv[i]; const double e = di > 0.0 ? scale / di : 0.0; return e * e; })); }
     const double floor_rel = (r0 > 0.0) ? sqrt(floor2) / r0 : 0.0;
     if (trace) fprintf(stderr, "ssrs_potential_solve: r0 %.3e attainable relative residual ~ %.3e\n", r0, floor_rel);
-    // (0.5: with floor/8 the recurrence residual kept falling for 2-4 more iterations after the true residual had
-    // flattened above the acceptance level — iterations the restart then had to repeat; 0.5..2 give the same counts:
-    // 26 instead of 30 at 1000 x 1200, 36 instead of 38 at 5000 x 6000)
-    const double floor_frac = getenv("SSRS_X_FLOORFRAC") ? atof(getenv("SSRS_X_FLOORFRAC")) : 0.5;
-    const double accept_frac = getenv("SSRS_X_ACCEPT") ? atof(getenv("SSRS_X_ACCEPT")) : 0.5;
+    // The fraction is set by accuracy, measured against the refined truth of the 1000 x 1200 / 10 m system
+    // (tests/golden/potential_truth10m.npz; tools/solver_truth_sweep.py, profiles/r02_solver_truth_sweep.txt): floor/2 leaves
+    // the float32 potential up to 5 ulp from the truth (27 iterations; 36 and 256 ms at 5000 x 6000), floor/8 2 ulp
+    // (30; 38, 268 ms), floor/16 1 ulp with < 1 % of the cells differing at all (32; 40, 280 ms), floor/32 1 ulp and
+    // 0.01 % (37; 44, 303 ms).  The reference's own unrefined SuperLU answer is 14 ulp off.  floor/16: tracks are steered
+    // by the potential's last float32 bits (SURVEY §0 findings 4 and 6), so the extra 9 % buys the 1-ulp answer.
+    const double floor_frac = getenv("SSRS_X_FLOORFRAC") ? atof(getenv("SSRS_X_FLOORFRAC")) : 0.0625;
+    const double accept_frac = getenv("SSRS_X_ACCEPT") ? atof(getenv("SSRS_X_ACCEPT")) : 0.0625;
     const double tol_eff = rtol > floor_frac * floor_rel ? rtol : floor_frac * floor_rel;
     int iters = 0, restarts = 0, converged = (r0 == 0.0);
     double best_true = 1.0;
@@ -1352,6 +1355,9 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         if (rel < best_true) best_true = rel;
     }
     { const double* xx = x; AMG_TRY(pfor_range(I0, I1, st, [=] SSRS_HD(i64 i) { phi[i] = (float)xx[i]; })); }     // movmodel.py:128
+    if (phi64 != nullptr) {         // diagnostics: the float64 iterate before rounding (single-rank solves)
+        const double* xx = x; AMG_TRY(pfor_range(I0, I1, st, [=] SSRS_HD(i64 i) { phi64[i] = xx[i]; }));
+    }
     if (comm != nullptr) {          // every rank returns the full raster (the stepping stage replicates the fields)
         i64 offs[SSRS_MAX_RANKS + 1];
         for (int q = 0; q <= H.nparts; ++q) offs[q] = H.lv[0].parts.lo[q] * (i64)sizeof(float);
@@ -1382,6 +1388,12 @@ int SOLVE_NAME(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     return ssrs::amg::solve_impl(K, rows, cols, bnodes_host, bvalues_host, n_bnodes, rtol, max_iter, phi, stats, nullptr, stream);
 }
 #ifndef SSRS_HOST_EMU
+extern "C" __attribute__((visibility("default")))
+int ssrs_potential_solve_f64(const float* K, int rows, int cols, const int64_t* bnodes_host, const double* bvalues_host,
+                             int64_t n_bnodes, double rtol, int max_iter, float* phi, double* phi64, ssrs_solve_stats* stats,
+                             void* stream) {
+    return ssrs::amg::solve_impl(K, rows, cols, bnodes_host, bvalues_host, n_bnodes, rtol, max_iter, phi, stats, nullptr, stream, phi64);
+}
 extern "C" __attribute__((visibility("default")))
 int ssrs_release_workspace(void) {
     if (!ssrs::par::arena(false).idle() || !ssrs::par::arena(true).idle()) { set_error("ssrs_release_workspace: a solve is in progress"); return SSRS_ERR_INVALID; }

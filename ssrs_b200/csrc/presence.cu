@@ -39,10 +39,50 @@ __global__ void __launch_bounds__(256) smooth_disk_kernel(const long long* __res
     }
 }
 
+// prefix[r][0] = 0, prefix[r][c + 1] = counts[r][0] + ... + counts[r][c]: one CTA per row, tiles of 256 columns scanned
+// with warp shuffles, the tile total carried in a register (exact integer sums)
+__global__ void __launch_bounds__(256) row_prefix_kernel(const unsigned* __restrict__ counts, int rows, int cols,
+                                                         long long* __restrict__ prefix) {
+    __shared__ long long warp_tot[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const unsigned* src = counts + (long long)r * cols;
+        long long* dst = prefix + (long long)r * (cols + 1);
+        long long carry = 0;
+        if (threadIdx.x == 0) dst[0] = 0;
+        for (int c0 = 0; c0 < cols; c0 += 256) {
+            const int c = c0 + threadIdx.x;
+            long long v = c < cols ? (long long)src[c] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            if (lane == 31) warp_tot[wid] = v;
+            __syncthreads();
+            long long before = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const long long wt = warp_tot[q]; total += wt; if (q < wid) before += wt; }
+            if (c < cols) dst[c + 1] = carry + before + v;
+            carry += total;
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace
 }  // namespace ssrs
 
 using namespace ssrs;
+
+extern "C" int ssrs_row_prefix_sums(const uint32_t* counts, int rows, int cols, long long* row_prefix, void* stream) {
+    SSRS_REQUIRE(counts && row_prefix, "ssrs_row_prefix_sums: NULL buffer");
+    SSRS_REQUIRE(rows > 0 && cols > 0, "ssrs_row_prefix_sums: bad sizes");
+    const int blocks = rows < sm_count() * 8 ? rows : sm_count() * 8;
+    row_prefix_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(counts, rows, cols, row_prefix);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
 
 extern "C" int ssrs_smooth_presence(const long long* row_prefix, int rows, int cols, int radius, float* out, void* stream) {
     SSRS_REQUIRE(row_prefix && out, "ssrs_smooth_presence: NULL buffer");

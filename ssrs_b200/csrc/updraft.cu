@@ -314,6 +314,21 @@ __global__ void threshold_kernel(const float* __restrict__ in, float* __restrict
     for (; i < n; i += stride) out[i] = threshold_fn(in[i], thr, thr_inv, inv_em1);
 }
 
+// compute_orographic_updraft (ssrs/layers.py:11-22) on already computed slope / aspect rasters (degrees):
+// max(V sin(slope) max(cos(aspect - dirn), 0), min_val), per-cell or uniform wind
+__global__ void orographic_kernel(const float* __restrict__ slope, const float* __restrict__ aspect,
+                                  const float* __restrict__ wspeed, const float* __restrict__ wdirn, float ws, float wd,
+                                  float min_val, float* __restrict__ out, int64_t n) {
+    const float d2r = 0.017453292519943295f;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float v = wspeed ? wspeed[i] : ws, dir = wdirn ? wdirn[i] : wd;
+        const float c = fmaxf(cosf((aspect[i] - dir) * d2r), 0.0f);
+        out[i] = fmaxf(v * (sinf(slope[i] * d2r) * c), min_val);
+    }
+}
+
 inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -391,6 +406,21 @@ extern "C" int ssrs_threshold(const float* in, float* out, int64_t n, float thre
     if (blocks > cap) blocks = cap;
     threshold_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         in, out, n, threshold, 1.0f / threshold, (float)(1.0 / (exp(1.0) - 1.0)));
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int ssrs_orographic_updraft(const float* slope_deg, const float* aspect_deg, const float* wspeed, const float* wdirn,
+                                       float uniform_wspeed, float uniform_wdirn_deg, float min_updraft, float* out, int64_t n,
+                                       void* stream) {
+    SSRS_REQUIRE(slope_deg && aspect_deg && out, "ssrs_orographic_updraft: NULL raster");
+    SSRS_REQUIRE(n >= 0, "ssrs_orographic_updraft: negative size");
+    if (n == 0) return SSRS_OK;
+    int64_t blocks = cdiv(n, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    orographic_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(slope_deg, aspect_deg, wspeed, wdirn, uniform_wspeed,
+                                                                                 uniform_wdirn_deg, min_updraft, out, n);
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
 }

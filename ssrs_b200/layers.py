@@ -67,15 +67,24 @@ def compute_aspect_degrees(z_mat, res: float):
 
 
 def compute_orographic_updraft(wspeed, wdirn, slope, aspect, min_updraft_val: float = 0.0):
-    """Reference `layers.py:11-22`.  Elementwise on already computed slope/aspect rasters; kept for API
-    parity (the Simulator uses the fused `updraft_fields`).  Runs as torch elementwise ops on the GPU."""
+    """Reference `layers.py:11-22`.  Elementwise on already computed slope/aspect rasters (`ssrs_orographic_updraft`);
+    kept for API parity — the Simulator uses the fused `updraft_fields`."""
     torch = N.require_cuda()
+    lib = N.load()
     s, was_tensor = _to_device(slope, torch)
     a, _ = _to_device(aspect, torch)
-    ws = float(wspeed) if np.isscalar(wspeed) else _to_device(wspeed, torch)[0]
-    wd = float(wdirn) if np.isscalar(wdirn) else _to_device(wdirn, torch)[0]
-    diff = torch.clamp(torch.cos((a - wd) * (np.pi / 180.0)), min=0.0)
-    out = torch.clamp(ws * (torch.sin(s * (np.pi / 180.0)) * diff), min=float(min_updraft_val))
+    if s.shape != a.shape:
+        raise ValueError("slope and aspect rasters differ in shape")
+    scalar_s, scalar_d = np.isscalar(wspeed), np.isscalar(wdirn)
+    ws = None if scalar_s else _to_device(wspeed, torch)[0]
+    wd = None if scalar_d else _to_device(wdirn, torch)[0]
+    for t in (ws, wd):
+        if t is not None and t.shape != s.shape:
+            raise ValueError("wind rasters must match the slope raster")
+    out = torch.empty_like(s)
+    N.check(lib.ssrs_orographic_updraft(N.ptr(s), N.ptr(a), N.ptr(ws), N.ptr(wd), float(wspeed) if scalar_s else 0.0,
+                                        float(wdirn) if scalar_d else 0.0, float(min_updraft_val), N.ptr(out), s.numel(),
+                                        N.current_stream()), "ssrs_orographic_updraft")
     return _back(out, was_tensor)
 
 

@@ -206,26 +206,70 @@ TRAJ_BUFFER_BYTES = 2 << 30        # device budget of one step-major trajectory 
 
 
 def _launch_steps(fields, rows, cols, start, n, track_id0, dirp_c, memory, nu, seed, u_t, ustride, traj, cap, traj_len,
-                  presence, total_steps, exact):
-    N.check(N.load().ssrs_step_tracks(N.ptr(fields), rows, cols, N.ptr(start), n, int(track_id0), dirp_c, int(memory),
-                                      float(nu), int(seed) & (2 ** 64 - 1), N.ptr(u_t), ustride, N.ptr(traj), cap,
-                                      N.ptr(traj_len), N.ptr(presence), N.ptr(total_steps), 1 if exact else 0,
-                                      N.current_stream()), "ssrs_step_tracks")
+                  presence, total_steps, exact, workspace=None, first_phase_steps=0):
+    lib = N.load()
+    args = (N.ptr(fields), rows, cols, N.ptr(start), n, int(track_id0), dirp_c, int(memory), float(nu),
+            int(seed) & (2 ** 64 - 1), N.ptr(u_t), ustride, N.ptr(traj), cap, N.ptr(traj_len), N.ptr(presence),
+            N.ptr(total_steps), 1 if exact else 0)
+    if workspace is None:
+        N.check(lib.ssrs_step_tracks(*args, N.current_stream()), "ssrs_step_tracks")
+    else:
+        N.check(lib.ssrs_step_tracks_phased(*args, N.ptr(workspace), workspace.numel() * workspace.element_size(),
+                                            int(first_phase_steps), N.current_stream()), "ssrs_step_tracks_phased")
+
+
+def walk_pays_off(track_count: int, grid_shape, memory_parameter: int = 1, scaling_parameter: float = 1.0) -> bool:
+    """Policy for the transition-table walk (`simulate_tracks_batch(walk=True)`): the table costs about as much as
+    stepping every (cell, previous move) pair twice, so it pays when the batch is expected to take several times more
+    steps than the grid has pairs.  Decided from the GLOBAL track count and the grid only, never from a rank's share:
+    the two stepping paths map random words to steps differently, so every rank of a sharded run must take the same
+    one for the result to be independent of the number of GPUs."""
+    rows, cols = int(grid_shape[0]), int(grid_shape[1])
+    if memory_parameter != 1 or scaling_parameter != 1.0:
+        return False
+    return int(track_count) * (rows + cols) // 2 >= 8 * rows * cols
+
+
+def build_transition_table(fields, move_dirn: float, out=None):
+    """Transition table of one (fields, direction): uint8 CUDA tensor of `ssrs_walk_table_bytes` bytes (64 B per cell),
+    written by `ssrs_transition_table` on the current stream.  Valid for track_dirn_restrict = 1, nu = 1."""
+    torch = N.require_cuda()
+    lib = N.load()
+    if fields is None or fields.dim() != 3 or fields.shape[2] != 2:
+        raise ValueError("fields must be the interleaved [rows, cols, 2] tensor of interleave_fields")
+    rows, cols = int(fields.shape[0]), int(fields.shape[1])
+    nbytes = int(lib.ssrs_walk_table_bytes(rows, cols))
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    elif out.numel() * out.element_size() < nbytes or not out.is_cuda:
+        raise ValueError("out is too small for the transition table")
+    dirp = get_directional_probs(move_dirn * np.pi / 180.0)
+    N.check(lib.ssrs_transition_table(N.ptr(fields), rows, cols, (C.c_double * 9)(*dirp.tolist()), N.ptr(out),
+                                      N.current_stream()), "ssrs_transition_table")
+    return out
 
 
 def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, memory_parameter: int = 1,
                           scaling_parameter: float = 1.0, fields=None, updraft_field=None, potential_field=None,
                           seed: int = 0, track_id0: int = 0, uniforms=None, record: bool = False,
                           traj_cap: Optional[int] = None, presence=None, total_steps=None,
-                          exact: bool = False) -> TrackBatchResult:
+                          exact: bool = False, walk: bool = False, table=None, workspace=None,
+                          first_phase_steps: int = 0, phased: bool = False) -> TrackBatchResult:
     """All tracks of one (case, realisation) in a single launch.
 
+    `start_rows`, `start_cols`: host arrays of start cells, or `start_rows` = a CUDA int32 tensor [n, 2] of (row, col)
+    with `start_cols=None` (no upload per launch).
     `fields` is a pre-interleaved device tensor from `interleave_fields`; alternatively give
     `updraft_field` and `potential_field`; with neither the 'drw' model runs (reference :298-299).
     `uniforms` ([n_tracks, stride] float64) switches on verification mode; otherwise Philox keyed by
     (seed, track_id0 + i, step).  `exact=True` forces the reference's exact operation order in production mode
     (verification mode always uses it).  `presence` (int32 CUDA tensor [rows, cols]) is accumulated into if given,
     else a fresh raster is created.
+    `phased=True` runs the launch in phases with survivor compaction (`ssrs_step_tracks_phased`: bit-identical results,
+    full warps; `workspace` as for the walk is created when not given).
+    `walk=True` takes the transition-table walk (`ssrs_walk_tracks`; needs fields, memory 1, nu 1, no uniforms, no
+    recording): `table` from `build_transition_table` is built here when not given, `workspace` (uint8 CUDA tensor of
+    `ssrs_walk_workspace_bytes(n)` bytes) likewise.  See `walk_pays_off` for when it is worth it.
     `record=True` stores the trajectories (step-major int16 [cap, n, 2]).  Track lengths are heavy-tailed (the longest
     of 100k tracks on 5000 x 6000 cells has ~1e5 points against a mean of 1e4), so without an explicit `traj_cap` the
     recording is two-pass: a first launch without trajectory or presence output yields the exact lengths (the random
@@ -235,20 +279,29 @@ def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, 
     torch = N.require_cuda()
     N.load()
     rows, cols = int(grid_shape[0]), int(grid_shape[1])
-    sr = np.asarray(start_rows).astype(np.int64).ravel()
-    sc = np.asarray(start_cols).astype(np.int64).ravel()
-    if sr.shape != sc.shape:
-        raise ValueError("start_rows and start_cols differ in length")
-    n = sr.size
-    if n and (sr.min() < 0 or sr.max() >= rows or sc.min() < 0 or sc.max() >= cols):
-        raise ValueError("start location outside the grid")
+    start = None
+    if isinstance(start_rows, torch.Tensor) and start_cols is None:
+        # already on the device: int32 [n, 2] (row, col), validated by whoever built it (no host round trip per launch)
+        start = start_rows
+        if not start.is_cuda or start.dtype != torch.int32 or start.dim() != 2 or start.shape[1] != 2 or not start.is_contiguous():
+            raise ValueError("a device start array must be a contiguous CUDA int32 tensor [n, 2]")
+        n = int(start.shape[0])
+    else:
+        sr = np.asarray(start_rows).astype(np.int64).ravel()
+        sc = np.asarray(start_cols).astype(np.int64).ravel()
+        if sr.shape != sc.shape:
+            raise ValueError("start_rows and start_cols differ in length")
+        n = sr.size
+        if n and (sr.min() < 0 or sr.max() >= rows or sc.min() < 0 or sc.max() >= cols):
+            raise ValueError("start location outside the grid")
     if fields is None and updraft_field is not None:
         if potential_field is None:
             raise ValueError("updraft_field without potential_field is not supported")
         fields = interleave_fields(updraft_field, potential_field)
     if fields is not None and tuple(fields.shape) != (rows, cols, 2):
         raise ValueError(f"fields shape {tuple(fields.shape)} does not match grid {(rows, cols)}")
-    start = torch.from_numpy(np.stack([sr, sc], axis=1).astype(np.int32)).to("cuda")
+    if start is None:
+        start = torch.from_numpy(np.stack([sr, sc], axis=1).astype(np.int32)).to("cuda")
     dirp = get_directional_probs(move_dirn * np.pi / 180.0)
     dirp_c = (C.c_double * 9)(*dirp.tolist())
     u_t, ustride = None, 0
@@ -258,6 +311,27 @@ def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, 
             raise ValueError("uniforms must be [n_tracks, stride]")
         u_t, ustride = torch.from_numpy(un).to("cuda"), un.shape[1]
     traj_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+    if walk:
+        if fields is None or memory_parameter != 1 or scaling_parameter != 1.0 or uniforms is not None or record or exact:
+            raise ValueError("walk=True needs fields, memory_parameter 1, scaling_parameter 1, Philox streams, "
+                             "record=False and exact=False")
+        lib = N.load()
+        if table is None:
+            table = build_transition_table(fields, move_dirn)
+        ws_bytes = int(lib.ssrs_walk_workspace_bytes(n))
+        if workspace is None:
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        if presence is None:
+            presence = torch.zeros((rows, cols), dtype=torch.int32, device="cuda")
+        if total_steps is None:
+            total_steps = torch.zeros(1, dtype=torch.int64, device="cuda")
+        N.check(lib.ssrs_walk_tracks(N.ptr(table), N.ptr(fields), rows, cols, N.ptr(start), n, int(track_id0), dirp_c,
+                                     int(seed) & (2 ** 64 - 1), N.ptr(traj_len), N.ptr(presence), N.ptr(total_steps),
+                                     N.ptr(workspace), workspace.numel() * workspace.element_size(),
+                                     int(first_phase_steps), N.current_stream()), "ssrs_walk_tracks")
+        res = TrackBatchResult(n, (rows, cols), None, traj_len, presence, total_steps, 0)
+        res._keepalive = (table, workspace, start)          # the launches are asynchronous
+        return res
     common = (fields, rows, cols, start, n, track_id0, dirp_c, memory_parameter, scaling_parameter, seed, u_t, ustride)
     traj = None
     cap = 0
@@ -275,8 +349,13 @@ def simulate_tracks_batch(move_dirn: float, start_rows, start_cols, grid_shape, 
         presence = torch.zeros((rows, cols), dtype=torch.int32, device="cuda")
     if total_steps is None:
         total_steps = torch.zeros(1, dtype=torch.int64, device="cuda")
-    _launch_steps(*common, traj, cap, traj_len, presence, total_steps, exact)
-    return TrackBatchResult(n, (rows, cols), traj, traj_len, presence, total_steps, cap)
+    if phased and workspace is None:
+        workspace = torch.empty(int(N.load().ssrs_walk_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    _launch_steps(*common, traj, cap, traj_len, presence, total_steps, exact, workspace if phased else None,
+                  first_phase_steps)
+    res = TrackBatchResult(n, (rows, cols), traj, traj_len, presence, total_steps, cap)
+    res._keepalive = (workspace, start, u_t)                # the launches are asynchronous
+    return res
 
 
 def record_tracks_packed(move_dirn: float, start_rows, start_cols, grid_shape, memory_parameter: int = 1,

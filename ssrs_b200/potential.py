@@ -27,7 +27,7 @@ class SolveStats(C.Structure):
                 "workspace_bytes": int(self.workspace_bytes)}
 
 
-def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict, comm=None):
+def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict, comm=None, want_f64=False):
     torch = N.require_cuda()
     lib = N.load()
     rows, cols = K_dev.shape
@@ -37,7 +37,15 @@ def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict, comm=None):
         raise ValueError("bnodes and benergy must be 1-D arrays of equal length")
     phi = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
     st = SolveStats()
-    if comm is None:
+    phi64 = None
+    if want_f64:
+        if comm is not None:
+            raise ValueError("the float64 iterate is available from single-rank solves only")
+        phi64 = torch.empty((rows, cols), dtype=torch.float64, device="cuda")
+        rc = lib.ssrs_potential_solve_f64(N.ptr(K_dev), rows, cols, bn.ctypes.data_as(C.POINTER(C.c_int64)),
+                                          bv.ctypes.data_as(C.POINTER(C.c_double)), bn.size, float(rtol), int(max_iter),
+                                          N.ptr(phi), N.ptr(phi64), C.byref(st), N.current_stream())
+    elif comm is None:
         rc = lib.ssrs_potential_solve(N.ptr(K_dev), rows, cols, bn.ctypes.data_as(C.POINTER(C.c_int64)),
                                       bv.ctypes.data_as(C.POINTER(C.c_double)), bn.size, float(rtol), int(max_iter),
                                       N.ptr(phi), C.byref(st), N.current_stream())
@@ -50,16 +58,19 @@ def _solve(K_dev, bnodes, bvals, rtol, max_iter, strict, comm=None):
         print(f"ssrs_b200: potential solve stopped at relative residual {stats['rel_residual']:.2e}")
     else:
         N.check(rc, "ssrs_potential_solve")
+    if want_f64:
+        stats["potential_f64"] = phi64
     return phi, stats
 
 
 def solve_potential_device(conductivity, move_dirn: float, rtol: float = 0.0, max_iter: int = 0, strict: bool = True,
-                           sharded: bool = False):
+                           sharded: bool = False, want_f64: bool = False):
     """K: CUDA float32 tensor [rows, cols] (or array-like) -> (phi CUDA float32 tensor, stats dict).
     Dirichlet sets come from `MovModel(move_dirn, shape).get_boundary_nodes()`.
     sharded=True (collective over the torch.distributed world; every rank passes the same K): the solve phase is
     row-sharded over the ranks with NCCL halo exchanges (`ssrs_potential_solve_sharded`); every rank gets the
-    full potential."""
+    full potential.
+    want_f64=True (single rank): stats["potential_f64"] holds the float64 iterate the potential was rounded from."""
     torch = N.require_cuda()
     from .movmodel import MovModel
     if isinstance(conductivity, torch.Tensor):
@@ -73,7 +84,7 @@ def solve_potential_device(conductivity, move_dirn: float, rtol: float = 0.0, ma
     if sharded:
         from . import dist as D
         comm = D.native_comm()
-    return _solve(K, bn, bv, rtol, max_iter, strict, comm)
+    return _solve(K, bn, bv, rtol, max_iter, strict, comm, want_f64)
 
 
 def solve_potential_nodes(conductivity, bnodes, benergy, rtol: float = 0.0, max_iter: int = 0, return_stats: bool = False):

@@ -15,8 +15,13 @@ def smooth_presence_counts(counts, radius: int):
     if c.dim() != 2:
         raise ValueError("counts must be a 2-D raster")
     rows, cols = c.shape
-    prefix = torch.zeros((rows, cols + 1), dtype=torch.int64, device="cuda")
-    torch.cumsum(c.to(torch.int64), dim=1, out=prefix[:, 1:])
+    if c.dtype not in (torch.int32, torch.uint32) or not c.is_contiguous():
+        if bool((c < 0).any()) or bool((c > 2 ** 32 - 1).any()):
+            raise ValueError("counts must be non-negative 32-bit values")
+        c = c.to(torch.int64).to(torch.int32).contiguous()      # bit pattern of the uint32 counts
+    prefix = torch.empty((rows, cols + 1), dtype=torch.int64, device="cuda")
+    lib = N.load()
+    N.check(lib.ssrs_row_prefix_sums(N.ptr(c), rows, cols, N.ptr(prefix), N.current_stream()), "ssrs_row_prefix_sums")
     out = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
     N.check(N.load().ssrs_smooth_presence(N.ptr(prefix), rows, cols, int(radius), N.ptr(out), N.current_stream()),
             "ssrs_smooth_presence")

@@ -389,9 +389,17 @@ class Simulator(Config):
         base = self.sim_seed if self.sim_seed >= 0 else int.from_bytes(os.urandom(4), 'little')
         return (base * 1_000_003 + case_index * 1009 + real_id) & (2 ** 63 - 1)
 
+    STEPS_IN_FLIGHT = 4                 # (case, realisation) stepping launches that may overlap on their own streams
+
     def simulate_tracks(self, save_tracks: Optional[bool] = None):
         """Simulate tracks (reference :332-386).  Presence counts are accumulated on the device during
-        stepping and kept per (case, realisation) in `self.presence_counts(id)`."""
+        stepping and kept per (case, realisation) in `self.presence_counts(id)`.
+
+        The reference steps one (case, realisation) after the other and waits for each pool.  Here every stepping launch
+        goes to one of a few side streams (phased launch, `ssrs_step_tracks_phased`) and its presence all-reduce to a
+        reduce stream, so the long tail of one launch — it lasts as long as its longest track — overlaps the next
+        case's potential solve and the bulk of its stepping; trajectories (when recorded) and files are produced after
+        the launches have drained."""
         torch = N.require_cuda()
         print(f'Movement model = {self.movement_model}')
         print(f'Updraft threshold = {self.updraft_threshold} m/s')
@@ -401,6 +409,15 @@ class Simulator(Config):
         n = len(starting_rows)
         lo, hi = self._d.shard_range(n, self._d.rank(), self._d.world_size())
         record = (n <= TRACKS_PKL_LIMIT) if save_tracks is None else bool(save_tracks)
+        if self.movement_model not in ('fluidflow', 'drw'):
+            raise ValueError(f'Invalid movement_model {self.movement_model!r}; options: fluidflow, drw')
+        phased = self.track_dirn_restrict == 1
+        slots = self.STEPS_IN_FLIGHT
+        streams = [torch.cuda.Stream() for _ in range(slots)]
+        reduce_stream = torch.cuda.Stream() if self._d.world_size() > 1 else None
+        in_slot = [None] * slots            # what the slot's last launch still reads (fields, workspace, result)
+        launched = []
+        t_all = time.time()
         for case_id in self._my_case_ids():
             ci = self.case_ids.index(case_id)
             for real_id, updraft in enumerate(self._load_updrafts_device(case_id)):
@@ -411,41 +428,58 @@ class Simulator(Config):
                 if self.movement_model == 'fluidflow':
                     self.get_directional_potential(updraft, case_id, real_id)
                     fields = interleave_fields(updraft, self._last_potential_device)
-                elif self.movement_model != 'drw':
-                    raise ValueError(f'Invalid movement_model {self.movement_model!r}; options: fluidflow, drw')
-                print(f'{id_str}: Simulating {self.track_count} tracks..', end="", flush=True)
-                t0 = time.time()
-                res = simulate_tracks_batch(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
-                                            self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
-                                            fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo)
-                presence = self._d.presence_allreduce(res.presence)        # ssrs_presence_allreduce (NCCL) when world > 1
-                steps = self._d.allreduce_sum(res._total.clone())
-                torch.cuda.synchronize()
-                self.timings['tracks_s'] = time.time() - t0
-                self.total_track_steps = int(steps.item())
-                print(f'took {_elapsed(t0)}', flush=True)
-                self._presence[id_str] = presence
-                fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
-                if record:
-                    # trajectories: a second, recording pass in chunks sized by the now known lengths (the longest track
-                    # is ~10x the mean, so one dense [longest, n] buffer would be mostly padding); the counter-based
-                    # streams make it repeat the counting pass step for step
-                    off, pts = record_tracks_packed(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
-                                                    self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
-                                                    fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
-                                                    lengths=res.traj_len.cpu().numpy())
-                    if n <= TRACKS_PKL_LIMIT:
-                        tracks = self._d.gather_tracks([a.copy() for a in trackio.unpack_tracks(off, pts)])
-                        if self._d.rank() == 0:
-                            self._writer.submit(trackio.save_tracks_pickle, fname, tracks)    # the reference's file (:383-386)
-                    else:
-                        # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
-                        suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
-                        self._writer.submit(trackio.save_tracks_packed, f'{fname}{suffix}', off, pts)
-                if self._d.rank() == 0:
-                    # counts of every run are kept on disk (uncompressed: compressing a 120 MB raster costs seconds), so
-                    # that a fresh Simulator over this run directory can build the presence map without the tracks
-                    self._writer.submit(np.savez, f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
+                print(f'{id_str}: Simulating {self.track_count} tracks..', flush=True)
+                k = len(launched) % slots
+                s = streams[k]
+                if in_slot[k] is not None:
+                    s.synchronize()                                   # the slot's previous launch has drained: its buffers go
+                    in_slot[k] = None
+                s.wait_stream(torch.cuda.current_stream())            # fields are ready
+                with torch.cuda.stream(s):
+                    res = simulate_tracks_batch(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
+                                                self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
+                                                fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
+                                                phased=phased)
+                    steps = res._total
+                    if reduce_stream is None:
+                        presence = res.presence
+                if reduce_stream is not None:
+                    reduce_stream.wait_stream(s)
+                    with torch.cuda.stream(reduce_stream):            # every rank issues the collectives in the same order
+                        presence = self._d.presence_allreduce(res.presence)      # ssrs_presence_allreduce (NCCL)
+                        steps = self._d.allreduce_sum(res._total.clone())
+                in_slot[k] = (fields, res)
+                launched.append((case_id, real_id, ci, id_str, fields if record else None, res, presence, steps))
+        for s in streams:
+            s.synchronize()
+        if reduce_stream is not None:
+            reduce_stream.synchronize()
+        self.timings['tracks_s'] = time.time() - t_all
+        print(f'Simulating tracks took {_elapsed(t_all)}', flush=True)
+        for case_id, real_id, ci, id_str, fields, res, presence, steps in launched:
+            self.total_track_steps = int(steps.item())
+            self._presence[id_str] = presence
+            fname = self._get_tracks_fname(case_id, real_id, self.mode_data_dir)
+            if record:
+                # trajectories: a second, recording pass in chunks sized by the now known lengths (the longest track
+                # is ~10x the mean, so one dense [longest, n] buffer would be mostly padding); the counter-based
+                # streams make it repeat the counting pass step for step
+                off, pts = record_tracks_packed(self.track_direction, starting_rows[lo:hi], starting_cols[lo:hi],
+                                                self.gridsize, self.track_dirn_restrict, self.track_stochastic_nu,
+                                                fields=fields, seed=self._track_seed(ci, real_id), track_id0=lo,
+                                                lengths=res.traj_len.cpu().numpy())
+                if n <= TRACKS_PKL_LIMIT:
+                    tracks = self._d.gather_tracks([a.copy() for a in trackio.unpack_tracks(off, pts)])
+                    if self._d.rank() == 0:
+                        self._writer.submit(trackio.save_tracks_pickle, fname, tracks)    # the reference's file (:383-386)
+                else:
+                    # large runs: packed offsets + points (trackio.py); one file per rank's block of track ids
+                    suffix = '' if self._d.world_size() == 1 else f'_part{self._d.rank()}of{self._d.world_size()}'
+                    self._writer.submit(trackio.save_tracks_packed, f'{fname}{suffix}', off, pts)
+            if self._d.rank() == 0:
+                # counts of every run are kept on disk (uncompressed: compressing a 120 MB raster costs seconds), so
+                # that a fresh Simulator over this run directory can build the presence map without the tracks
+                self._writer.submit(np.savez, f'{fname}_presence_counts.npz', counts=presence.cpu().numpy())
         self.flush()
 
     def load_tracks(self, case_id: Optional[str] = None, real_id: int = 0):

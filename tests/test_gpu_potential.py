@@ -91,6 +91,45 @@ def test_full_size_residual_and_bounds():
         assert rel.max() < 5e-7, (r0, rel.max())      # float32 rounding of phi alone gives ~6e-8 * O(1)
 
 
+def test_full_size_maximum_principle_and_plateaus():
+    """(5000, 6000) at 10 m.  The reference's tracks are steered by float32 rounding plateaus of the potential (SURVEY §0
+    finding 4), and a damaged potential shows up as spurious local minima that trap tracks (finding 6).  On the solver's
+    float64 iterate BEFORE rounding the discrete maximum principle must hold: a free cell is a weighted mean of its
+    neighbours, so no free interior cell may lie strictly below all eight of them.  After rounding to float32 most
+    cells sit on plateaus (no strictly lower neighbour) — reported, with a sanity band, because that fraction is what
+    sets the track lengths at this resolution."""
+    import torch
+    from ssrs_b200 import layers
+    from ssrs_b200.potential import solve_potential_device
+    from ssrs_b200.synth import synthetic_dem
+    rows, cols, res = 5000, 6000, 10.0
+    z = torch.from_numpy(synthetic_dem(rows, cols, res)).cuda()
+    K = layers.updraft_fields(z, res, 10.0, 270.0, 0.75, want=("updraft",))["updraft"]
+    phi, stats = solve_potential_device(K, 0.0, want_f64=True)
+    p64 = stats["potential_f64"]
+    assert float((p64.float() - phi).abs().max().item()) == 0.0        # phi is exactly the rounded iterate
+
+    def census(p):
+        c = p[1:-1, 1:-1]
+        strict_min = torch.ones_like(c, dtype=torch.bool)
+        has_lower = torch.zeros_like(c, dtype=torch.bool)
+        for dr in (-1, 0, 1):
+            for dc in (-1, 0, 1):
+                if dr or dc:
+                    nb = p[1 + dr:rows - 1 + dr, 1 + dc:cols - 1 + dc]
+                    strict_min &= nb > c
+                    has_lower |= nb < c
+        return int(strict_min.sum().item()), float((~has_lower).float().mean().item())
+
+    m64, flat64 = census(p64)
+    m32, flat32 = census(phi)
+    print(f"5000x6000: float64 iterate: {m64} strict interior minima, {100 * flat64:.4f} % of cells without a lower neighbour; "
+          f"float32: {m32} strict minima, {100 * flat32:.2f} % without a lower neighbour; {stats['iterations']} iterations")
+    assert m64 == 0
+    assert flat64 < 1e-3
+    assert 0.2 < flat32 < 0.9
+
+
 def test_errors():
     from ssrs_b200 import movmodel as mm
     from ssrs_b200._native import NativeError

@@ -243,3 +243,32 @@ def test_errors():
         mm.get_starting_indices(10, (5, 55, 1, 2), "spiral", (60., 50.), 100.)
     r = mm.simulate_tracks_batch(0.0, [], [], (50, 60), updraft_field=U, potential_field=U)
     assert r.total_steps == 0 and int(r.presence.sum()) == 0
+
+
+@pytest.mark.parametrize("mem,nu,dirn,exact", [(1, 1.0, 0.0, False), (1, 1.0, 135.0, False), (1, 2.0, 90.0, False),
+                                               (1, 1.0, 0.0, True), (2, 1.0, 315.0, False)])
+def test_phased_launch_is_bit_identical(mem, nu, dirn, exact):
+    """ssrs_step_tracks_phased (survivors compacted every few steps — a cut every 32 steps here, dozens of phases — and
+    the default schedule) against the C oracle and the single launch: same lengths, presence, step total, and with
+    recording the same trajectories.  memory 2 runs as one launch behind the same entry point."""
+    from ssrs_b200 import movmodel as mm
+    rows, cols = 200, 240
+    U = _fields(rows, cols, 100.0)
+    P = O.solve_potential(U.astype(np.float64), dirn)
+    rng = np.random.RandomState(3)
+    n = 3000
+    starts = np.stack([rng.randint(0, rows, n), rng.randint(0, cols, n)], 1).astype(np.int32)
+    ref = OC.step_tracks(U, P, (rows, cols), starts, dirn, mem, nu, seed=1234, track_id0=17, nthreads=8, fast=not exact)
+    f = mm.interleave_fields(U, P)
+    for first in (32, 0):
+        res = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, fields=f, seed=1234,
+                                       track_id0=17, exact=exact, phased=True, first_phase_steps=first)
+        assert res.total_steps == ref["total_steps"]
+        assert np.array_equal(res.traj_len.cpu().numpy(), ref["traj_len"])
+        assert np.array_equal(res.presence.cpu().numpy(), ref["presence"])
+    cap = int(ref["traj_len"].max())
+    rec = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, fields=f, seed=1234,
+                                   track_id0=17, exact=exact, phased=True, first_phase_steps=32, record=True, traj_cap=cap)
+    one = mm.simulate_tracks_batch(dirn, starts[:, 0], starts[:, 1], (rows, cols), mem, nu, fields=f, seed=1234,
+                                   track_id0=17, exact=exact, record=True, traj_cap=cap)
+    assert np.array_equal(rec.traj.cpu().numpy(), one.traj.cpu().numpy())
