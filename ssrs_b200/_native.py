@@ -35,6 +35,7 @@ EXPORTS = {
     "ssrs_gaussian_blur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                      C.c_void_p, C.c_void_p]),
     "ssrs_release_workspace": (C.c_int, []),
+    "ssrs_reserve_workspace": (C.c_int, [C.c_int, C.c_int]),
     "ssrs_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ssrs_comm_create_nccl": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ssrs_comm_destroy": (C.c_int, [C.c_void_p]),

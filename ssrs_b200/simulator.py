@@ -165,6 +165,12 @@ class Simulator(Config):
         if tuple(z.shape) != self.gridsize:
             raise ValueError(f"elevation shape {tuple(z.shape)} does not match gridsize {self.gridsize}")
         self._elev = z
+        if self.movement_model == 'fluidflow':
+            # one-time costs of stage 2 paid here instead of inside the first solve: the solver's workspace arena and, in a
+            # multi-process run whose solves are row-sharded, the library's NCCL communicator (5 s at 8 GPUs)
+            N.check(N.load().ssrs_reserve_workspace(ysize, xsize), "ssrs_reserve_workspace")
+            if _dist.world_size() > 1 and not self._case_parallel:
+                _dist.native_comm()
         self._writer = _ArtefactWriter()
         self._force_potential = bool(force_potential)
         self._oro_cache: Dict[str, "torch.Tensor"] = {}       # float32 orographs kept on the device (what the .npy holds)
@@ -411,7 +417,10 @@ class Simulator(Config):
         record = (n <= TRACKS_PKL_LIMIT) if save_tracks is None else bool(save_tracks)
         if self.movement_model not in ('fluidflow', 'drw'):
             raise ValueError(f'Invalid movement_model {self.movement_model!r}; options: fluidflow, drw')
-        phased = self.track_dirn_restrict == 1
+        # several launches in flight: phased launches (survivors compacted, so a launch's tail leaves the SMs to the next
+        # one); a single launch is fastest stepped to the end in one go (its tracks run alone, one per lane)
+        n_launches = len(self._my_case_ids()) * (1 + int(self.thermals_realization_count))
+        phased = self.track_dirn_restrict == 1 and n_launches > 1
         slots = self.STEPS_IN_FLIGHT
         streams = [torch.cuda.Stream() for _ in range(slots)]
         reduce_stream = torch.cuda.Stream() if self._d.world_size() > 1 else None
