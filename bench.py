@@ -368,18 +368,11 @@ class StepRing:
 
 
 def phase_launches(rows, cols, mode):
-    """Kernel launches of one stepping call (the phase schedule of stepper.cuh)."""
+    """Kernel launches of one stepping call."""
+    from ssrs_b200 import _native as N
     if mode == "single":
         return 1
-    kmax = int(np.ceil(rows / 2 * cols / 2))
-    c, n = max(1024, min(rows, cols)), 0
-    while n < 63:
-        c = (c + 3) & ~3
-        if c >= kmax:
-            break
-        n += 1
-        c += max(c // 4, 4)
-    return n + 1 + (1 if mode == "walk" else 0)
+    return int(N.load().ssrs_step_phase_count(rows, cols, 0)) + (1 if mode == "walk" else 0)
 
 
 def main():
@@ -422,8 +415,9 @@ def main():
     up, pot, finfo = build_fields_gpu(a, torch, world, w, check_sharded=True)
     fields = mm.interleave_fields(up, pot)
     total = torch.zeros(1, dtype=torch.int64, device="cuda")
-    warm = max(a.warmup, 3)
     ring = StepRing(torch, shape, n_rank, a.streams, a.mode, world)
+    # every slot of the ring is warmed once: a stream's first launches allocate (and so synchronise) in its memory pool
+    warm = max(a.warmup, 3, ring.slots)
     start_h = torch.from_numpy(np.stack([sr, sc], 1).astype(np.int32)).pin_memory()
     start_d = start_h.to("cuda")                 # the device-timed steps read the start cells from HBM like the fields
 
@@ -478,6 +472,8 @@ def main():
     pot_h.copy_(pot)
     slots = ring.slots
     pres_h = [torch.empty(shape, dtype=torch.int32).pin_memory() for _ in range(slots)]
+    dev_in = [(torch.empty(shape, dtype=torch.float32, device="cuda"), torch.empty(shape, dtype=torch.float32, device="cuda"),
+               torch.empty((n_rank, 2), dtype=torch.int32, device="cuda")) for _ in range(slots)]      # landing buffers per slot
     tot_e2e = torch.zeros(1, dtype=torch.int64, device="cuda")
     copied = [None] * slots
 
@@ -489,9 +485,10 @@ def main():
         if copied[k] is not None:
             s.wait_event(copied[k])              # the slot's previous map has left for the host
         with torch.cuda.stream(s):
-            u_d = up_h.to("cuda", non_blocking=True)
-            p_d = pot_h.to("cuda", non_blocking=True)
-            st_d = start_h.to("cuda", non_blocking=True)
+            u_d, p_d, st_d = dev_in[k]
+            u_d.copy_(up_h, non_blocking=True)
+            p_d.copy_(pot_h, non_blocking=True)
+            st_d.copy_(start_h, non_blocking=True)
             f_d = mm.interleave_fields(u_d, p_d)
         ring.issue(i, f_d, st_d, None, seed, lo, tot_e2e)          # steps, (all-reduces)
         out_stream = ring.reduce_stream if world > 1 else s
@@ -502,7 +499,7 @@ def main():
         copied[k] = ev
         ring.free[k] = ev
 
-    for i in range(2):
+    for i in range(slots):
         e2e_step(i, a.seed)
     ring.join()
     barrier()

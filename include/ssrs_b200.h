@@ -218,6 +218,9 @@ SSRS_API int ssrs_step_tracks(const float* fields, int rows, int cols,
  * streams' launches.  Same arguments and bit-identical results as ssrs_step_tracks (the random stream is keyed by
  * track id and step); workspace = ssrs_walk_workspace_bytes(n_tracks) bytes, caller-owned, reusable once `stream`
  * has passed the call. */
+/* Number of phases (= kernel launches) ssrs_step_tracks_phased / ssrs_walk_tracks use on a rows x cols grid. */
+SSRS_API int ssrs_step_phase_count(int rows, int cols, int first_phase_steps);
+
 SSRS_API int ssrs_step_tracks_phased(const float* fields, int rows, int cols,
                      const int32_t* start_rc, int64_t n_tracks, int64_t track_id0,
                      const double* dirprob9_host, int memory, double nu,

@@ -49,6 +49,7 @@ EXPORTS = {
     "ssrs_walk_tracks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                    C.POINTER(C.c_double), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_int, C.c_void_p]),
+    "ssrs_step_phase_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ssrs_step_tracks_phased": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                           C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -490,6 +490,14 @@ int step_tracks_impl(const float* fields, int rows, int cols, const int32_t* sta
 }
 }  // namespace
 
+extern "C" int ssrs_step_phase_count(int rows, int cols, int first_phase_steps) {
+    // kernel launches of one phased stepping call (host arithmetic only; bench.py counts its launches with it)
+    if (rows < 5 || cols < 5) return 0;
+    const double km = ceil((double)rows / 2 * (double)cols / 2);
+    int caps[kMaxPhases];
+    return phase_caps(rows, cols, km > 2147483647.0 ? 2147483647 : (int)km, first_phase_steps, caps);
+}
+
 extern "C" int ssrs_step_tracks(const float* fields, int rows, int cols, const int32_t* start_rc, int64_t n_tracks,
                                 int64_t track_id0, const double* dirprob9_host, int memory, double nu, uint64_t seed,
                                 const double* uniforms, int64_t uniforms_stride, int16_t* traj, int64_t traj_cap,

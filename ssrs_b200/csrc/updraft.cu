@@ -12,7 +12,8 @@
 // kept rolling in registers; outputs leave as float4 stores (512 B contiguous per warp and row).
 //
 // Numerics: Horn sums are formed differences-first, which is exact in fp32 for
-// float32 DEMs, so `dz_dx == 0` fires on the same cells as the float64 reference; the updraft itself is
+// float32 DEMs, so `dz_dx == 0` fires on the same cells as the float64 reference; two adjacent cells share every
+// packed FFMA2/FMUL2 (the kernel is issue-bound, not HBM-bound); the updraft itself is
 // evaluated without inverse trig:  sin(atan h) = h / sqrt(1+h^2),
 // cos(aspect - wdir) = -(gy cos(wdir) + gx' sin(wdir)) / hypot(gx', gy)   with gx' = (gx==0 ? 1e-10 : gx).
 #include "common.cuh"
@@ -73,50 +74,101 @@ __device__ __forceinline__ float threshold_fn(float w, float thr, float thr_inv,
     return thr * inv_em1 * (p * x);
 }
 
+// ---- two cells at a time: packed float32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100a; constants ride as broadcast immediates) ----
+// The stencil kernels are issue-bound (ncu: 74 % issue-active at 64 % of HBM); two thirds of a cell's instructions are
+// FMUL / FFMA / FADD, and a packed instruction does two cells' worth.  Each lane of a packed operation rounds exactly
+// like the scalar one.
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 pk(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ F2 pk1(float x) { return pk(x, x); }
+__device__ __forceinline__ void upk(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+
 // atan(t) for t in [0, 1]: t * P(t^2), degree-6 minimax fit (max error 3.2e-7 rad = 1.8e-5 degrees,
 // i.e. ~1e-6 of the slope range and ~5e-8 of the aspect range; the contract is 1e-5 of each field's maximum).
-__device__ __forceinline__ float atan01(float t) {
-    const float s = t * t;
-    float p = 0.006811788771301508f;
-    p = fmaf(p, s, -0.0336042158305645f);
-    p = fmaf(p, s, 0.07962367683649063f);
-    p = fmaf(p, s, -0.132333442568779f);
-    p = fmaf(p, s, 0.19807817041873932f);
-    p = fmaf(p, s, -0.3331736922264099f);
-    p = fmaf(p, s, 0.9999961256980896f);
-    return p * t;
+__device__ __forceinline__ F2 atan01_2(F2 t) {
+    const F2 s = mul2(t, t);
+    F2 p = pk1(0.006811788771301508f);
+    p = fma2(p, s, pk1(-0.0336042158305645f));
+    p = fma2(p, s, pk1(0.07962367683649063f));
+    p = fma2(p, s, pk1(-0.132333442568779f));
+    p = fma2(p, s, pk1(0.19807817041873932f));
+    p = fma2(p, s, pk1(-0.3331736922264099f));
+    p = fma2(p, s, pk1(0.9999961256980896f));
+    return mul2(p, t);
 }
 
-// One cell.  Arguments are the nine DEM samples named as in layers.py:80-88 would index them:
-// n* = row r+1, m* = row r, s* = row r-1 ; *w = col c-1, *c = col c, *e = col c+1.
-// Square roots and quotients go through MUFU.RSQ / MUFU.RCP (<= 2 ulp), inverse tangents through atan01.
+// threshold_fn on both lanes (layers.py:171-180)
+__device__ __forceinline__ void threshold2(float w0, float w1, float thr, float thr_inv, float thr_scale, float& u0, float& u1) {
+    const F2 t = mul2(pk(w0, w1), pk1(thr_inv));
+    const F2 t2 = mul2(t, t);
+    const F2 x = mul2(mul2(t2, t2), t);
+    F2 p = pk1(0.00031020541791804135f);
+    p = fma2(p, x, pk1(0.0012223972007632256f));
+    p = fma2(p, x, pk1(0.008451635017991066f));
+    p = fma2(p, x, pk1(0.041624147444963455f));
+    p = fma2(p, x, pk1(0.16667389869689941f));
+    p = fma2(p, x, pk1(0.4999995529651642f));
+    p = fma2(p, x, pk1(1.0f));
+    float m0, m1;
+    upk(mul2(mul2(p, x), pk1(thr_scale)), m0, m1);
+    u0 = !(w0 > 0.01f) ? 0.0f : (w0 > thr ? w0 : m0);
+    u1 = !(w1 > 0.01f) ? 0.0f : (w1 > thr ? w1 : m1);
+}
+
+// Two horizontally adjacent cells (a, b) from their Horn gradients gx = dz_dx (derivative along axis 0, rows) and
+// gy = dz_dy (along axis 1, columns), layers.py:89-90.  Square roots and quotients go through MUFU.RSQ / MUFU.RCP
+// (<= 2 ulp), inverse tangents through atan01_2.
 template <bool WANT_ANGLES>
-__device__ __forceinline__ void cell(float sw_, float sc_, float se_, float mw_, float me_,
-                                     float nw_, float nc_, float ne_,
-                                     float inv8res, float V, float sinw, float cosw,
-                                     float& slope, float& aspect, float& oro) {
-    // dz_dx: derivative along axis 0 (rows) ; dz_dy: along axis 1 (cols)   (layers.py:89-90)
-    const float gx = ((ne_ - se_) + 2.0f * (nc_ - sc_) + (nw_ - sw_)) * inv8res;
-    const float gy = ((se_ - sw_) + 2.0f * (me_ - mw_) + (ne_ - nw_)) * inv8res;
-    const float h2 = fmaf(gx, gx, gy * gy);
-    const float h = h2 > 1e-30f ? h2 * rsqrt_approx(h2) : 0.0f;
-    const float gxa = (gx == 0.0f) ? 1e-10f : gx;                         // layers.py:124
-    const float rha = rsqrt_approx(fmaf(gxa, gxa, gy * gy));
-    const float cosd = -(gy * cosw + gxa * sinw) * rha;                   // cos(aspect - wdir)
-    const float sins = h * rsqrt_approx(1.0f + h2);                             // sin(atan(h))
-    oro = fmaxf(0.0f, V * sins * fmaxf(0.0f, cosd));                      // layers.py:19-22
+__device__ __forceinline__ void cell2(float gxa_, float gya_, float gxb_, float gyb_, F2 V, F2 sinw, F2 cosw,
+                                      float& slope_a, float& slope_b, float& aspect_a, float& aspect_b, float& oro_a, float& oro_b) {
+    const F2 gx = pk(gxa_, gxb_), gy = pk(gya_, gyb_);
+    const F2 gy2 = mul2(gy, gy);
+    const F2 h2 = fma2(gx, gx, gy2);
+    float h2a, h2b;
+    upk(h2, h2a, h2b);
+    const F2 hraw = mul2(h2, pk(rsqrt_approx(h2a), rsqrt_approx(h2b)));
+    float ha, hb;
+    upk(hraw, ha, hb);
+    ha = h2a > 1e-30f ? ha : 0.0f;
+    hb = h2b > 1e-30f ? hb : 0.0f;
+    const float gxaa = (gxa_ == 0.0f) ? 1e-10f : gxa_;                    // layers.py:124
+    const float gxab = (gxb_ == 0.0f) ? 1e-10f : gxb_;
+    const F2 gxa = pk(gxaa, gxab);
+    float q2a, q2b;
+    upk(fma2(gxa, gxa, gy2), q2a, q2b);
+    const F2 rha = pk(rsqrt_approx(q2a), rsqrt_approx(q2b));
+    // cos(aspect - wdir) = -(gy cos(wdir) + gx' sin(wdir)) / hypot(gx', gy)
+    float cda, cdb;
+    upk(mul2(fma2(gxa, sinw, mul2(gy, cosw)), rha), cda, cdb);
+    float opa, opb;
+    upk(add2(h2, pk1(1.0f)), opa, opb);
+    const F2 sins = mul2(pk(ha, hb), pk(rsqrt_approx(opa), rsqrt_approx(opb)));      // sin(atan(h))
+    float oa, ob;
+    upk(mul2(mul2(V, sins), pk(fmaxf(0.0f, -cda), fmaxf(0.0f, -cdb))), oa, ob);
+    oro_a = fmaxf(0.0f, oa);                                              // layers.py:19-22
+    oro_b = fmaxf(0.0f, ob);
     if (WANT_ANGLES) {
-        const bool steep = h > 1.0f;
-        float a = atan01(steep ? rcp_approx(h) : h);
-        slope = (steep ? 1.5707963267948966f - a : a) * 57.29577951308232f;
-        const float ay = fabsf(gy), ax = fabsf(gxa);
-        float p = atan01(fminf(ay, ax) * rcp_approx(fmaxf(ay, ax)));
-        p = ay > ax ? 1.5707963267948966f - p : p;
-        const float ang = ((gy < 0.0f) != (gxa < 0.0f)) ? -p : p;         // atan(dz_dy / dz_dx)
-        aspect = 180.0f - ang * 57.29577951308232f + copysignf(90.0f, gxa);   // layers.py:125-127
+        const bool steep_a = ha > 1.0f, steep_b = hb > 1.0f;
+        float a0, a1;
+        upk(atan01_2(pk(steep_a ? rcp_approx(ha) : ha, steep_b ? rcp_approx(hb) : hb)), a0, a1);
+        a0 = steep_a ? 1.5707963267948966f - a0 : a0;
+        a1 = steep_b ? 1.5707963267948966f - a1 : a1;
+        upk(mul2(pk(a0, a1), pk1(57.29577951308232f)), slope_a, slope_b);
+        const float aya = fabsf(gya_), axa = fabsf(gxaa), ayb = fabsf(gyb_), axb = fabsf(gxab);
+        float p0, p1;
+        upk(atan01_2(mul2(pk(fminf(aya, axa), fminf(ayb, axb)), pk(rcp_approx(fmaxf(aya, axa)), rcp_approx(fmaxf(ayb, axb))))), p0, p1);
+        p0 = aya > axa ? 1.5707963267948966f - p0 : p0;
+        p1 = ayb > axb ? 1.5707963267948966f - p1 : p1;
+        const float ang0 = ((gya_ < 0.0f) != (gxaa < 0.0f)) ? -p0 : p0;   // atan(dz_dy / dz_dx)
+        const float ang1 = ((gyb_ < 0.0f) != (gxab < 0.0f)) ? -p1 : p1;
+        // aspect = 180 - ang * 57.29... + copysign(90, gx')              layers.py:125-127
+        upk(fma2(pk(ang0, ang1), pk1(-57.29577951308232f), pk(180.0f + copysignf(90.0f, gxaa), 180.0f + copysignf(90.0f, gxab))),
+            aspect_a, aspect_b);
     } else {
-        slope = 0.0f;
-        aspect = 0.0f;
+        slope_a = slope_b = aspect_a = aspect_b = 0.0f;
     }
 }
 
@@ -191,17 +243,29 @@ __device__ __forceinline__ void compute_tile(const UpdraftParams& p, const float
                 for (int j = 0; j < 4; ++j) sincospif(wd[j] * (1.0f / 180.0f), &sn[j], &cs[j]);
             }
             const bool edge_row = (r == 0) || (r == p.rows - 1);
+            // Horn gradients of the four cells, differences first (exact for float32 DEMs): dz_dx along rows, dz_dy
+            // along columns (layers.py:80-90)
+            float gx[4], gy[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int c = c0 + j;
+                gx[j] = ((N[j + 2] - S[j + 2]) + 2.0f * (N[j + 1] - S[j + 1]) + (N[j] - S[j])) * p.inv8res;
+                gy[j] = ((S[j + 2] - S[j]) + 2.0f * (M[j + 2] - M[j]) + (N[j + 2] - N[j])) * p.inv8res;
+            }
+            const float thr_scale = p.thr * p.inv_em1;
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
                 if (want_angles)
-                    cell<true>(S[j], S[j + 1], S[j + 2], M[j], M[j + 2], N[j], N[j + 1], N[j + 2],
-                               p.inv8res, V[j], sn[j], cs[j], sl[j], as[j], oro[j]);
+                    cell2<true>(gx[j], gy[j], gx[j + 1], gy[j + 1], pk(V[j], V[j + 1]), pk(sn[j], sn[j + 1]), pk(cs[j], cs[j + 1]),
+                                sl[j], sl[j + 1], as[j], as[j + 1], oro[j], oro[j + 1]);
                 else
-                    cell<false>(S[j], S[j + 1], S[j + 2], M[j], M[j + 2], N[j], N[j + 1], N[j + 2],
-                                p.inv8res, V[j], sn[j], cs[j], sl[j], as[j], oro[j]);
-                if (edge_row || c == 0 || c >= p.cols - 1) { sl[j] = 0.0f; as[j] = 0.0f; oro[j] = 0.0f; }
-                up[j] = threshold_fn(oro[j], p.thr, p.thr_inv, p.inv_em1);
+                    cell2<false>(gx[j], gy[j], gx[j + 1], gy[j + 1], pk(V[j], V[j + 1]), pk(sn[j], sn[j + 1]), pk(cs[j], cs[j + 1]),
+                                 sl[j], sl[j + 1], as[j], as[j + 1], oro[j], oro[j + 1]);
+#pragma unroll
+                for (int q = j; q < j + 2; ++q) {
+                    const int c = c0 + q;
+                    if (edge_row || c == 0 || c >= p.cols - 1) { sl[q] = 0.0f; as[q] = 0.0f; oro[q] = 0.0f; }
+                }
+                threshold2(oro[j], oro[j + 1], p.thr, p.thr_inv, thr_scale, up[j], up[j + 1]);
             }
             store4<VEC>(p.slope, idx, c0, p.cols, sl[0], sl[1], sl[2], sl[3]);
             store4<VEC>(p.aspect, idx, c0, p.cols, as[0], as[1], as[2], as[3]);

@@ -123,3 +123,32 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "track-steps/sec" and d["value"] > 0
     # the reference's own modules when they are reachable (/root/reference here, the staged oracle/_ref on the GPU box)
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_phase_schedule_and_walk_policy():
+    """Host arithmetic behind the phased launches: the schedule is geometric (x1.25) from one crossing of the short side up
+    to max_moves; the walk policy depends on the global track count and the grid only."""
+    from ssrs_b200 import _native, movmodel as mm
+    lib = _native.load()
+    assert lib.ssrs_step_phase_count(5000, 6000, 0) == 34          # 5000, 6252, ... < 7.5e6, + the open-ended last phase
+    assert lib.ssrs_step_phase_count(120, 160, 0) == 8             # first cut at 1024 steps, max_moves = 4800
+    assert lib.ssrs_step_phase_count(120, 160, 64) > 15
+    assert lib.ssrs_step_phase_count(3, 3, 0) == 0
+    assert mm.walk_pays_off(100_000, (5000, 6000)) and not mm.walk_pays_off(1000, (500, 600))
+    assert not mm.walk_pays_off(10 ** 6, (5000, 6000), memory_parameter=2)
+    assert lib.ssrs_walk_table_bytes(5000, 6000) == 5000 * 6000 * 64
+    assert lib.ssrs_walk_workspace_bytes(1000) >= 2 * 1000 * 16
+
+
+def test_reference_staging(tmp_path, monkeypatch):
+    """oracle/ref_loader.stage_reference copies the reference's two hot-path modules byte for byte (git-ignored
+    oracle/_ref/), and the loader finds them there when /root/reference is absent (the GPU box)."""
+    from oracle import ref_loader as R
+    if not os.path.isfile("/root/reference/ssrs/movmodel.py"):
+        pytest.skip("reference tree not present")
+    monkeypatch.setattr(R, "STAGED_ROOT", str(tmp_path / "_ref"))
+    assert R.stage_reference()
+    for m in R.HOT_PATH_MODULES:
+        assert open(tmp_path / "_ref" / "ssrs" / m, "rb").read() == open(f"/root/reference/ssrs/{m}", "rb").read()
+    gi = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in gi
