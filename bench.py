@@ -70,8 +70,8 @@ except (OSError, KeyError, ValueError):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ssrs_b200", choices=["ssrs_b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config3", "config4", "config5"])
     ap.add_argument("--rows", type=int, default=0)
@@ -557,7 +557,7 @@ def main():
             "roofline_l2": ({"bound": "l2", "achieved": STEP_L2_BYTES_PER_STEP * (steps_rank / a.steps) / (per_launch_ms * 1e-3) / 1e9,
                              "peak": L2_PEAK_GBS, "unit": "GB/s",
                              "frac": STEP_L2_BYTES_PER_STEP * (steps_rank / a.steps) / (per_launch_ms * 1e-3) / 1e9 / L2_PEAK_GBS,
-                             "source": "lts__t_bytes.sum per track-step from the ncu capture, L2 peak measured by tools/l2_peak.py "
+                             "source": "lts__t_bytes.sum per track-step from the ncu capture, L2 peak measured by tools/ubench/l2bw.cu "
                                        "(profiles/r02_stepping_traffic.json)"} if STEP_L2_BYTES_PER_STEP and L2_PEAK_GBS else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / a.steps},

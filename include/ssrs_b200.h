@@ -269,6 +269,12 @@ SSRS_API int ssrs_interleave_fields(const float* updraft, const float* potential
 SSRS_API int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len,
                          int64_t n_tracks, int rows, int cols, uint32_t* presence, void* stream);
 
+/* Step-major trajectories as written by ssrs_step_tracks -> the packed on-disk form (ssrs_b200/trackio.py): point k of
+ * track t goes to points[offsets[t] + k] for k < traj_len[t]; offsets int64 [n_tracks] = exclusive running sum of
+ * traj_len (all lengths <= traj_cap); points int16 [sum traj_len][2]. */
+SSRS_API int ssrs_pack_trajectories(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len, const int64_t* offsets,
+                           int64_t n_tracks, int16_t* points, void* stream);
+
 /* Running sums of a uint32 count raster along each row, the input of ssrs_smooth_presence:
  * row_prefix int64 [rows][cols+1], row_prefix[r][0] = 0, row_prefix[r][c+1] = counts[r][0] + ... + counts[r][c]. */
 SSRS_API int ssrs_row_prefix_sums(const uint32_t* counts, int rows, int cols, long long* row_prefix, void* stream);

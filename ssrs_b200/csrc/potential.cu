@@ -978,6 +978,27 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
     return fine_jacobi32(F, r0, r1, rhs, H.xf, out, om, st);
 }
 
+#ifndef SSRS_HOST_EMU
+// Gauss-Jordan on the coarsest level in ONE launch: a single CTA walks the pivots, the n x n matrices stay in L2
+// (n <= 512: 2 MB each).  Per element the same operations in the same order as the pivot-by-pivot loop below, which
+// it replaces on the device (that loop costs two launches per pivot: 318 launches for the 159 coarsest rows of a
+// 5000 x 6000 grid).
+__global__ void __launch_bounds__(1024) dense_inverse_kernel(double* __restrict__ D, double* __restrict__ I, double* __restrict__ colk,
+                                                             double* __restrict__ rowD, double* __restrict__ rowI, int n) {
+    for (int k = 0; k < n; ++k) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { colk[i] = D[(size_t)i * n + k]; rowD[i] = D[(size_t)k * n + i]; rowI[i] = I[(size_t)k * n + i]; }
+        __syncthreads();
+        const double p = colk[k];
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e / n, j = e - i * n;
+            if (i == k) { D[e] = rowD[j] / p; I[e] = rowI[j] / p; }
+            else { const double f = colk[i] / p; if (f != 0.0) { D[e] -= f * rowD[j]; I[e] -= f * rowI[j]; } }
+        }
+        __syncthreads();
+    }
+}
+#endif
+
 int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
     const i64 n = C.n;
     double *D, *I, *colk, *rowD, *rowI;
@@ -992,6 +1013,15 @@ int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
         I[i * n + i] = 1.0;
         for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) D[i * n + g.col[k]] = g.val[k];
     }));
+#ifndef SSRS_HOST_EMU
+    if (n <= 512) {
+        dense_inverse_kernel<<<1, 1024, 0, st>>>(D, I, colk, rowD, rowI, (int)n);
+        AMG_TRY(cudaGetLastError() == cudaSuccess ? 0 : -1);
+        AMG_TRY(sync(st));
+        H.cinv = I; H.cn = n;
+        return SSRS_OK;
+    }
+#endif
     for (i64 k = 0; k < n; ++k) {       // Gauss-Jordan; diagonally dominant M-matrix: no pivoting needed
         AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) { colk[i] = D[i * n + k]; rowD[i] = D[k * n + i]; rowI[i] = I[k * n + i]; }));
         AMG_TRY(pfor(n * n, st, [=] SSRS_HD(i64 e) {

@@ -367,6 +367,18 @@ __global__ void presence_from_traj_kernel(const short2* __restrict__ traj, long 
     }
 }
 
+// step-major trajectories -> packed points: point k of track t goes to points[offsets[t] + k]
+__global__ void pack_traj_kernel(const short2* __restrict__ traj, long long traj_cap, const int* __restrict__ len,
+                                 const long long* __restrict__ offsets, long long n_tracks, short2* __restrict__ points) {
+    const long long total = traj_cap * n_tracks;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long k = i / n_tracks, t = i - k * n_tracks;
+        if (k < (long long)__ldg(len + t)) points[__ldg(offsets + t) + k] = traj[i];
+    }
+}
+
 }  // namespace
 }  // namespace ssrs
 
@@ -543,6 +555,21 @@ extern "C" int ssrs_presence_counts(const int16_t* traj, int64_t traj_cap, const
     if (blocks > cap) blocks = cap;
     presence_from_traj_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const short2*>(traj), traj_cap, traj_len, n_tracks, rows, cols, presence);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int ssrs_pack_trajectories(const int16_t* traj, int64_t traj_cap, const int32_t* traj_len, const int64_t* offsets,
+                                      int64_t n_tracks, int16_t* points, void* stream) {
+    SSRS_REQUIRE(traj && traj_len && offsets && points, "ssrs_pack_trajectories: NULL buffer");
+    SSRS_REQUIRE(traj_cap > 0 && n_tracks >= 0, "ssrs_pack_trajectories: bad sizes");
+    if (n_tracks == 0) return SSRS_OK;
+    long long blocks = cdiv(traj_cap * n_tracks, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pack_traj_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const short2*>(traj), traj_cap, traj_len, reinterpret_cast<const long long*>(offsets), n_tracks,
+        reinterpret_cast<short2*>(points));
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
 }

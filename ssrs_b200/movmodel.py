@@ -167,20 +167,19 @@ class TrackBatchResult:
 
     def packed(self):
         """(offsets int64 [n + 1], points int16 [total, 2]) on the host — the packed on-disk form (trackio.py),
-        gathered on the device from the step-major trajectory buffer."""
+        gathered on the device from the step-major trajectory buffer (`ssrs_pack_trajectories`)."""
         torch = N.require_cuda()
-        self._checked_lengths()
-        lens = self.traj_len.to(torch.int64)
-        offsets = torch.zeros(self.n_tracks + 1, dtype=torch.int64, device=lens.device)
-        torch.cumsum(lens, 0, out=offsets[1:])
-        points_parts = []
-        chunk = max(1, (1 << 28) // max(1, self.traj_cap))           # bound the boolean mask to ~256 MB
-        for lo in range(0, self.n_tracks, chunk):
-            hi = min(self.n_tracks, lo + chunk)
-            mask = torch.arange(self.traj_cap, device=lens.device)[None, :] < lens[lo:hi, None]
-            points_parts.append(self.traj[:, lo:hi].permute(1, 0, 2)[mask].cpu())
-        points = torch.cat(points_parts) if points_parts else torch.zeros((0, 2), dtype=torch.int16)
-        return offsets.cpu().numpy(), points.numpy()
+        lens_h = self._checked_lengths().astype(np.int64)
+        offsets_h = np.zeros(self.n_tracks + 1, dtype=np.int64)
+        np.cumsum(lens_h, out=offsets_h[1:])
+        total = int(offsets_h[-1])
+        if total == 0:
+            return offsets_h, np.zeros((0, 2), dtype=np.int16)
+        offsets = torch.from_numpy(offsets_h[:-1].copy()).to("cuda")
+        points = torch.empty((total, 2), dtype=torch.int16, device="cuda")
+        N.check(N.load().ssrs_pack_trajectories(N.ptr(self.traj), self.traj_cap, N.ptr(self.traj_len), N.ptr(offsets),
+                                                self.n_tracks, N.ptr(points), N.current_stream()), "ssrs_pack_trajectories")
+        return offsets_h, points.cpu().numpy()
 
 
 def interleave_fields(updraft, potential):
