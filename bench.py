@@ -712,12 +712,14 @@ def reference_arm(a, w, world):
     n_total = w["n_total"]
     sr, sc = start_cells(w, n_total, a.seed)
     use_ref = ref_loader.available()
-    # bounded sample per step: calibrate on a few tracks, then size a step for ~4 s of wall time
+    # bounded sample per step: one track per process costs `dt0` of wall time (the reference's pool pickles its closure —
+    # the two rasters — once per task chunk, simulator.py:361-369, which dominates small samples); a step gets as many
+    # rounds of that as fit a total budget of ~150 s for the whole run
     if use_ref:
         probe = min(n_total, threads)
-        rate0, steps0, dt0, procs = cpu_reference_rate(U, P, sr, sc, probe, threads, a.seed)
-        mean_len = max(1.0, steps0 / probe)
-        n_sample = a.cpu_sample_tracks or int(max(threads, min(n_total, 4.0 * rate0 / mean_len)))
+        _, steps0, dt0, procs = cpu_reference_rate(U, P, sr, sc, probe, threads, a.seed)
+        per_step = 150.0 / max(1, a.steps + min(a.warmup, 1))
+        n_sample = a.cpu_sample_tracks or int(min(n_total, probe * max(1, int(per_step / max(dt0, 1e-3)))))
         run = lambda lo: cpu_reference_rate(U, P, sr[lo:], sc[lo:], n_sample, threads, a.seed)[:3]
         kind, how = "reference", (f"unmodified ssrs/movmodel.py generate_simulated_tracks through multiprocess.Pool({threads}).map "
                                   f"(ssrs/simulator.py:360-369)")
