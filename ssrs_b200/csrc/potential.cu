@@ -260,18 +260,41 @@ struct Level {
 };
 
 #define AMG_TRY(expr) do { if ((expr) != 0) { set_error("ssrs_potential_solve: device operation failed: %s", #expr); return SSRS_ERR_CUDA; } } while (0)
+#define AMG_RC(expr) do { const int rc_ = (expr); if (rc_) return rc_; } while (0)
 #define AMG_ALLOC(var, T, count) do { var = pool.get<T>(count); if (!var) { set_error("ssrs_potential_solve: out of device memory (%lld x %zu B)", (long long)(count), sizeof(T)); return SSRS_ERR_CUDA; } } while (0)
+
+// ---- distributed setup (row-sharded solve) --------------------------------------------------------------
+// While a level is distributed every rank builds ITS rows of the hierarchy only: aggregates never straddle a slab
+// boundary, so matching, numbering, member lists, Galerkin rows and the ELL slices of a part depend on that part's rows
+// alone — plus the aggregate ids of the ghost rows (one halo exchange per level) and three tiny exchanges of per-part
+// integers (aggregate counts, referenced index ranges, entry counts).  Per-row results are the same operations on the
+// same operands as in the redundant setup, so the hierarchy — and with it every iterate — is bit-identical to it.
+struct SetupDist {
+    const ssrs_comm* comm = nullptr;   // nullptr: this level is built in full by every caller (one GPU, or a redundant level)
+    int rank = 0, size = 1;
+    stream_t st = nullptr;
+    bool on() const { return comm != nullptr; }
+    // v[q] for q != rank must be 0 on entry: on return every rank holds all parts' values (exact below 2^53)
+    int gather(double* v, int count) const {
+        if (comm == nullptr) return 0;
+        if (comm->allreduce_sum(comm->ctx, v, count, (void*)st) != 0) { set_error("ssrs_potential_solve: all-reduce failed during setup"); return SSRS_ERR_CUDA; }
+        return 0;
+    }
+};
 
 // ---- coarsening: pairwise matching + joins ---------------------------------------------------------
 template <class G>
-int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_rounds, Parts* next, stream_t st) {
+int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_rounds, Parts* next, stream_t st,
+            const SetupDist D = SetupDist()) {
     const i64 n = g.size();
+    // rows this caller works on: its own slab of a distributed level, else the whole level
+    const i64 i0 = D.on() ? g.parts.lo[D.rank] : 0, i1 = D.on() ? g.parts.lo[D.rank + 1] : n;
     float* rowmax; int *mate, *best, *root, *root2;
     Pool tmp(st, true);
     rowmax = tmp.get<float>(n); mate = tmp.get<int>(n); best = tmp.get<int>(n); root = tmp.get<int>(n); root2 = tmp.get<int>(n);
     if (!rowmax || !mate || !best || !root || !root2) { set_error("ssrs_potential_solve: out of device memory in coarsen"); return SSRS_ERR_CUDA; }
     const float th = (float)theta;
-    AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+    AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
         float m = 0.0f;
         if (!g.excluded(i)) {
             i64 k0, k1; g.range(i, k0, k1);
@@ -281,7 +304,7 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
         mate[i] = g.excluded(i) ? -2 : -1;
     }));
     for (int rnd = 0; rnd < rounds; ++rnd) {
-        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+        AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
             int bj = -1;
             if (mate[i] == -1) {
                 float bw = 0.0f; unsigned bh = 0;
@@ -300,17 +323,17 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
             }
             best[i] = bj;
         }));
-        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+        AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
             const int b = best[i];
             if (b >= 0 && best[b] == (int)i) mate[i] = b;
         }));
     }
-    AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+    AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
         const int m = mate[i];
         root[i] = m >= 0 ? ((int)i < m ? (int)i : m) : (m == -2 ? -2 : -1);
     }));
     for (int jr = 0; jr < join_rounds; ++jr) {
-        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+        AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
             int out = root[i];
             if (out == -1) {
                 int bj = -1, btwo = 0; float bw = 0.0f; unsigned bh = 0;
@@ -338,20 +361,34 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
     if (!flag) { set_error("ssrs_potential_solve: out of device memory in coarsen"); return SSRS_ERR_CUDA; }
     {
         int* rt = root;
-        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+        AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
             if (rt[i] == -1) rt[i] = (int)i;                  // singleton
             flag[i] = (rt[i] == (int)i) ? 1 : 0;
         }));
     }
-    i64 nc = 0;
-    AMG_TRY(exclusive_scan_i64(flag, n, &nc, st));
-    // ownership of the coarse nodes: numbering follows the roots, so every part's aggregates are contiguous
+    i64 nc = 0, clo = 0, chi = 0;      // coarse nodes in total; this caller's range of them
     next->n = g.parts.n;
-    next->lo[0] = 0;
-    next->lo[next->n] = nc;
-    for (int p = 1; p < g.parts.n; ++p) {
-        if (g.parts.lo[p] >= n) next->lo[p] = nc;
-        else AMG_TRY(copy_d2h(&next->lo[p], flag + g.parts.lo[p], sizeof(i64), st));
+    if (D.on()) {
+        // number the own slab's roots, then shift by the aggregates of the parts before it
+        i64 nc_local = 0;
+        AMG_TRY(exclusive_scan_i64(flag + i0, i1 - i0, &nc_local, st));
+        double cnts[SSRS_MAX_RANKS] = {0.0};
+        cnts[D.rank] = (double)nc_local;
+        AMG_RC(D.gather(cnts, D.size));
+        next->lo[0] = 0;
+        for (int p = 0; p < D.size; ++p) next->lo[p + 1] = next->lo[p] + (i64)cnts[p];
+        nc = next->lo[D.size]; clo = next->lo[D.rank]; chi = next->lo[D.rank + 1];
+        if (clo > 0) { const i64 base = clo; AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { flag[i] += base; })); }
+    } else {
+        AMG_TRY(exclusive_scan_i64(flag, n, &nc, st));
+        // ownership of the coarse nodes: numbering follows the roots, so every part's aggregates are contiguous
+        next->lo[0] = 0;
+        next->lo[next->n] = nc;
+        for (int p = 1; p < g.parts.n; ++p) {
+            if (g.parts.lo[p] >= n) next->lo[p] = nc;
+            else AMG_TRY(copy_d2h(&next->lo[p], flag + g.parts.lo[p], sizeof(i64), st));
+        }
+        chi = nc;
     }
     AMG_ALLOC(L.agg, int, n);
     AMG_ALLOC(L.memptr, i64, nc + 1);
@@ -363,23 +400,24 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
     AMG_TRY(dev_zero(cnt, sizeof(int) * (size_t)(nc + 1), st));
     {
         const int* rt = root;
-        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+        AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
             const int r = rt[i];
             const int c = r >= 0 ? (int)flag[r] : -1;
             agg[i] = c;
             if (c >= 0) atomic_add_int(cnt + c, 1);
         }));
     }
-    AMG_TRY(pfor(nc + 1, st, [=] SSRS_HD(i64 I) { memptr[I] = I < nc ? (i64)cnt[I] : 0; }));
+    // member lists of the own aggregates (offsets local to this caller's `mem`)
+    AMG_TRY(pfor_range(clo, chi + 1, st, [=] SSRS_HD(i64 I) { memptr[I] = I < chi ? (i64)cnt[I] : 0; }));
     i64 total = 0;
-    AMG_TRY(exclusive_scan_i64(memptr, nc + 1, &total, st));
+    AMG_TRY(exclusive_scan_i64(memptr + clo, chi - clo + 1, &total, st));
     AMG_TRY(dev_zero(cnt, sizeof(int) * (size_t)(nc + 1), st));
-    AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+    AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
         const int c = agg[i];
         if (c >= 0) { const int slot = atomic_add_int(cnt + c, 1); mem[memptr[c] + slot] = (int)i; }
     }));
     // members in ascending order -> deterministic Galerkin sums
-    AMG_TRY(pfor(nc, st, [=] SSRS_HD(i64 I) {
+    AMG_TRY(pfor_range(clo, chi, st, [=] SSRS_HD(i64 I) {
         const i64 a = memptr[I], b = memptr[I + 1];
         for (i64 p = a + 1; p < b; ++p) {
             const int v = mem[p];
@@ -393,26 +431,29 @@ int coarsen(const G g, Level& L, Pool& pool, double theta, int rounds, int join_
 }
 
 // ---- Galerkin coarse operator for piecewise-constant prolongation ---------------------------------------
+// [clo, chi): the coarse rows this caller builds (its own aggregates of a distributed level — `agg` must then hold the
+// ghost rows' ids too —, else all of them); C.rowptr / col / val are local to the caller in the distributed case.
 template <class G>
-int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
+int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st, i64 clo = 0, i64 chi = -1) {
     const i64 nc = L.nc;
+    if (chi < 0) chi = nc;
     const int* agg = L.agg; const i64* memptr = L.memptr; const int* mem = L.mem;
     Pool tmp(st, true);
     i64* off = tmp.get<i64>(nc + 1);
     int* len = tmp.get<int>(nc);
     if (!off || !len) { set_error("ssrs_potential_solve: out of device memory in galerkin"); return SSRS_ERR_CUDA; }
-    AMG_TRY(pfor(nc + 1, st, [=] SSRS_HD(i64 I) {
+    AMG_TRY(pfor_range(clo, chi + 1, st, [=] SSRS_HD(i64 I) {
         i64 ub = 0;
-        if (I < nc)
+        if (I < chi)
             for (i64 p = memptr[I]; p < memptr[I + 1]; ++p) { i64 k0, k1; g.range(mem[p], k0, k1); ub += (k1 - k0) + 1; }
         off[I] = ub;
     }));
     i64 scratch_n = 0;
-    AMG_TRY(exclusive_scan_i64(off, nc + 1, &scratch_n, st));
+    AMG_TRY(exclusive_scan_i64(off + clo, chi - clo + 1, &scratch_n, st));
     int* scol = tmp.get<int>(scratch_n);
     double* sval = tmp.get<double>(scratch_n);
     if (!scol || !sval) { set_error("ssrs_potential_solve: out of device memory in galerkin (%lld entries)", (long long)scratch_n); return SSRS_ERR_CUDA; }
-    AMG_TRY(pfor(nc, st, [=] SSRS_HD(i64 I) {
+    AMG_TRY(pfor_range(clo, chi, st, [=] SSRS_HD(i64 I) {
         int* cj = scol + off[I];
         double* cv = sval + off[I];
         int cnt = 0;
@@ -445,13 +486,13 @@ int galerkin(const G g, const Level& L, Level& C, Pool& pool, stream_t st) {
     }));
     AMG_ALLOC(C.rowptr, i64, nc + 1);
     i64* rowptr = C.rowptr;
-    AMG_TRY(pfor(nc + 1, st, [=] SSRS_HD(i64 I) { rowptr[I] = I < nc ? (i64)len[I] : 0; }));
+    AMG_TRY(pfor_range(clo, chi + 1, st, [=] SSRS_HD(i64 I) { rowptr[I] = I < chi ? (i64)len[I] : 0; }));
     i64 nnz = 0;
-    AMG_TRY(exclusive_scan_i64(rowptr, nc + 1, &nnz, st));
+    AMG_TRY(exclusive_scan_i64(rowptr + clo, chi - clo + 1, &nnz, st));
     AMG_ALLOC(C.col, int, nnz);
     AMG_ALLOC(C.val, double, nnz);
     int* col = C.col; double* val = C.val;
-    AMG_TRY(pfor(nc, st, [=] SSRS_HD(i64 I) {
+    AMG_TRY(pfor_range(clo, chi, st, [=] SSRS_HD(i64 I) {
         const i64 s = off[I], d = rowptr[I];
         for (int q = 0; q < len[I]; ++q) { col[d + q] = scol[s + q]; val[d + q] = sval[s + q]; }
     }));
@@ -780,10 +821,16 @@ int exchange_ghosts(const Hierarchy& H, int l, void* vec, size_t esize) {
     return SSRS_OK;
 }
 
-// CSR (float64, diagonal stored) -> sliced ELL (float32)
-int build_ell(Level& L, Pool& pool, stream_t st) {
+// CSR (float64, diagonal stored) -> sliced ELL (float32).  With D.on() (a distributed level during setup) only the
+// caller's own rows are laid out — slice offsets are local to the caller, a slice that straddles a part boundary is
+// sized by the caller's rows in it — and the per-part quantities every rank needs are exchanged: whether the packed
+// entry format applies (decided for the level as a whole, as in the redundant setup) and the index range each part's
+// rows reference.
+int build_ell(Level& L, Pool& pool, stream_t st, const SetupDist D = SetupDist()) {
     const CsrGraph g = csr_of(L);
     const i64 n = L.n, slices = (n + 31) / 32;
+    const i64 i0 = D.on() ? L.parts.lo[D.rank] : 0, i1 = D.on() ? L.parts.lo[D.rank + 1] : n;
+    const i64 s0 = i0 / 32, s1 = i1 > i0 ? (i1 + 31) / 32 : s0;          // slices that hold own rows
     AMG_ALLOC(L.sptr, i64, slices + 1);
     AMG_ALLOC(L.excess, float, n);
     AMG_ALLOC(L.dinv, float, n);
@@ -792,32 +839,52 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
     AMG_ALLOC(L.t32, real, n);
     AMG_ALLOC(L.r32, real, n);
     i64* sptr = L.sptr; float* excess = L.excess; float* dinv = L.dinv;
-    AMG_TRY(pfor(slices + 1, st, [=] SSRS_HD(i64 s) {
+    AMG_TRY(pfor_range(s0, s1 + 1, st, [=] SSRS_HD(i64 s) {
         i64 width = 0;
-        if (s < slices)
+        if (s < s1)
             for (i64 i = s * 32; i < s * 32 + 32 && i < n; ++i) {
+                if (i < i0 || i >= i1) continue;
                 i64 len = 0;
                 for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) len += (g.col[k] != (int)i);
                 if (len > width) width = len;
             }
         sptr[s] = width * 32;
     }));
+    if (D.on() && i1 - i0 >= 64) {
+        // a slice shared with a neighbour gets the width the whole slice has (the order in which a row's entries are
+        // summed depends on it, and that order is to be the redundant setup's)
+        const bool sh_lo = (i0 & 31) != 0, sh_hi = (i1 & 31) != 0 && i1 < n;
+        i64 wl = 0, wh = 0;
+        if (sh_lo) AMG_TRY(copy_d2h(&wl, sptr + s0, sizeof(i64), st));
+        if (sh_hi) AMG_TRY(copy_d2h(&wh, sptr + s1 - 1, sizeof(i64), st));
+        AMG_TRY(sync(st));
+        double v[2 * SSRS_MAX_RANKS] = {0.0};
+        v[2 * D.rank] = (double)wl; v[2 * D.rank + 1] = (double)wh;
+        AMG_RC(D.gather(v, 2 * D.size));
+        if (sh_lo && D.rank > 0 && (i64)v[2 * (D.rank - 1) + 1] > wl) { wl = (i64)v[2 * (D.rank - 1) + 1]; AMG_TRY(copy_h2d(sptr + s0, &wl, sizeof(i64), st)); }
+        if (sh_hi && D.rank + 1 < D.size && (i64)v[2 * (D.rank + 1)] > wh) { wh = (i64)v[2 * (D.rank + 1)]; AMG_TRY(copy_h2d(sptr + s1 - 1, &wh, sizeof(i64), st)); }
+        AMG_TRY(sync(st));
+    } else if (D.on()) {
+        double v[2 * SSRS_MAX_RANKS] = {0.0};        // keep the collective call sequence identical on every rank
+        AMG_RC(D.gather(v, 2 * D.size));
+    }
     i64 total = 0;
-    AMG_TRY(exclusive_scan_i64(sptr, slices + 1, &total, st));
+    AMG_TRY(exclusive_scan_i64(sptr + s0, s1 - s0 + 1, &total, st));
     // packed 4-byte entries when every column lies within +-32767 of its row (node numbering follows the raster, so
     // this holds unless a raster row has more than ~1e5 cells); else {int32 column, float32 value}
     double far_entries = 0.0;
-    AMG_TRY(preduce_sum(n, st, &far_entries, [=] SSRS_HD(i64 i) {
+    AMG_TRY(preduce_sum_range(i0, i1, st, &far_entries, [=] SSRS_HD(i64 i) {
         double cnt = 0.0;
         for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) { const i64 dlt = (i64)g.col[k] - i; cnt += (dlt > 32767 || dlt < -32767) ? 1.0 : 0.0; }
         return cnt;
     }));
+    AMG_RC(D.gather(&far_entries, 1));
     const bool packed = g_ell_packed && far_entries == 0.0;
     L.ell_entries = total;
     if (packed) { AMG_ALLOC(L.epack, unsigned, total); }
     else { AMG_ALLOC(L.ecol, int, total); AMG_ALLOC(L.eval, float, total); }
     int* ecol = L.ecol; float* eval = L.eval; unsigned* epack = L.epack;
-    AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+    AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
         const i64 s = i >> 5;
         i64 p = sptr[s] + (i & 31);
         const i64 p1 = sptr[s + 1];
@@ -836,6 +903,18 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
         excess[i] = (float)(d + off);
         dinv[i] = (float)(1.0 / d);
     }));
+    if (D.on() && s1 > s0) {
+        // rows of a straddling slice that belong to the neighbours: their lanes must read as empty entries
+        const i64 a0 = s0 * 32, a1 = (s1 * 32 < n ? s1 * 32 : n);
+        AMG_TRY(pfor_range(a0, a1, st, [=] SSRS_HD(i64 i) {
+            if (i >= i0 && i < i1) return;
+            const i64 s = i >> 5;
+            for (i64 p = sptr[s] + (i & 31); p < sptr[s + 1]; p += 32) {
+                if (packed) epack[p] = 0u;
+                else { ecol[p] = (int)i; eval[p] = 0.0f; }
+            }
+        }));
+    }
     // row-sharded solve: the index range each part's rows reference (its own range plus the ghost zones)
     const Parts P = L.parts;
     for (int q = 0; q < P.n; ++q) { L.ref_lo[q] = P.lo[q]; L.ref_hi[q] = P.lo[q + 1]; }
@@ -846,7 +925,7 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
         i64 init[2 * SSRS_MAX_RANKS];
         for (int q = 0; q < P.n; ++q) { init[q] = L.ref_lo[q]; init[P.n + q] = L.ref_hi[q]; }
         AMG_TRY(copy_h2d(ref, init, sizeof(i64) * 2 * (size_t)P.n, st));
-        AMG_TRY(pfor(n, st, [=] SSRS_HD(i64 i) {
+        AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) {
             i64 lo = i, hi = i;
             for (i64 k = g.rowptr[i]; k < g.rowptr[i + 1]; ++k) { const i64 j = g.col[k]; lo = j < lo ? j : lo; hi = j > hi ? j : hi; }
             const int q = parts_owner(P, i);
@@ -855,6 +934,12 @@ int build_ell(Level& L, Pool& pool, stream_t st) {
         }));
         AMG_TRY(copy_d2h(init, ref, sizeof(i64) * 2 * (size_t)P.n, st));
         AMG_TRY(sync(st));
+        if (D.on()) {            // every rank knows its own part's range: share them
+            double v[2 * SSRS_MAX_RANKS] = {0.0};
+            v[D.rank] = (double)init[D.rank]; v[P.n + D.rank] = (double)init[P.n + D.rank];
+            AMG_RC(D.gather(v, 2 * P.n));
+            for (int q = 0; q < 2 * P.n; ++q) init[q] = (i64)v[q];
+        }
         for (int q = 0; q < P.n; ++q) { L.ref_lo[q] = init[q]; L.ref_hi[q] = init[P.n + q]; }
     }
     return SSRS_OK;
@@ -875,8 +960,6 @@ int coarse_solve(Hierarchy& H, Level& C, stream_t st) {
                           [=] SSRS_HD(i64 i, int lane) { double s = 0.0; for (i64 j = lane; j < n; j += 32) s += inv[i * n + j] * (double)b[j]; return s; },
                           [=] SSRS_HD(i64 i, double total) { x[i] = (real)total; });
 }
-
-#define AMG_RC(expr) do { const int rc_ = (expr); if (rc_) return rc_; } while (0)
 
 // out = M^-1 rhs: one V(nu, nu) cycle from a zero guess; rhs must be zero at Dirichlet nodes.  In the row-sharded
 // solve rhs/out are valid on the owned rows (rhs ghost rows are refreshed here; out's are not), levels below
@@ -985,14 +1068,18 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
 // 5000 x 6000 grid).
 __global__ void __launch_bounds__(1024) dense_inverse_kernel(double* __restrict__ D, double* __restrict__ I, double* __restrict__ colk,
                                                              double* __restrict__ rowD, double* __restrict__ rowI, int n) {
+    __shared__ double s_p;
     for (int k = 0; k < n; ++k) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) { colk[i] = D[(size_t)i * n + k]; rowD[i] = D[(size_t)k * n + i]; rowI[i] = I[(size_t)k * n + i]; }
+        if (threadIdx.x == 0) s_p = D[(size_t)k * n + k];
         __syncthreads();
-        const double p = colk[k];
+        const double p = s_p;
+        // the row factors colk[i] / p once per pivot instead of once per element (same quotient, n instead of n^2 divisions)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { colk[i] = D[(size_t)i * n + k] / p; rowD[i] = D[(size_t)k * n + i]; rowI[i] = I[(size_t)k * n + i]; }
+        __syncthreads();
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
             const int i = e / n, j = e - i * n;
             if (i == k) { D[e] = rowD[j] / p; I[e] = rowI[j] / p; }
-            else { const double f = colk[i] / p; if (f != 0.0) { D[e] -= f * rowD[j]; I[e] -= f * rowI[j]; } }
+            else { const double f = colk[i]; if (f != 0.0) { D[e] -= f * rowD[j]; I[e] -= f * rowI[j]; } }
         }
         __syncthreads();
     }
@@ -1034,6 +1121,43 @@ int dense_inverse(Hierarchy& H, const Level& C, Pool& pool, stream_t st) {
     AMG_TRY(sync(st));
     H.cinv = I; H.cn = n;
     return SSRS_OK;
+}
+
+// Distributed setup, first redundant level: its CSR rows were built by their owners (local row pointers); every rank
+// now needs all of them.  Row lengths are all-gathered and scanned, the owners' entries land at their global offsets
+// and are all-gathered in place; the level's ELL form is then rebuilt over all rows.
+int gather_level(Hierarchy& H, Level& L, Pool& pool, stream_t st) {
+    const ssrs_comm* comm = H.comm;
+    const Parts P = L.parts;
+    const int R = comm->rank;
+    const i64 n = L.n, lo = P.lo[R], hi = P.lo[R + 1];
+    i64* rp;
+    AMG_ALLOC(rp, i64, n + 1);
+    { const i64* lrp = L.rowptr; AMG_TRY(pfor_range(lo, hi, st, [=] SSRS_HD(i64 i) { rp[i] = lrp[i + 1] - lrp[i]; })); }
+    i64 offs[SSRS_MAX_RANKS + 1];
+    for (int q = 0; q <= P.n; ++q) offs[q] = P.lo[q] * (i64)sizeof(i64);
+    if (comm->allgather(comm->ctx, rp, offs, (void*)st) != 0) { set_error("ssrs_potential_solve: all-gather of row lengths failed"); return SSRS_ERR_CUDA; }
+    AMG_TRY(pfor_range(n, n + 1, st, [=] SSRS_HD(i64 i) { rp[i] = 0; }));
+    i64 nnz = 0;
+    AMG_TRY(exclusive_scan_i64(rp, n + 1, &nnz, st));
+    i64 starts[SSRS_MAX_RANKS + 1];
+    for (int q = 0; q <= P.n; ++q) {
+        if (P.lo[q] >= n) starts[q] = nnz;
+        else AMG_TRY(copy_d2h(&starts[q], rp + P.lo[q], sizeof(i64), st));
+    }
+    AMG_TRY(sync(st));
+    int* col; double* val;
+    AMG_ALLOC(col, int, nnz);
+    AMG_ALLOC(val, double, nnz);
+    if (starts[R + 1] - starts[R] != L.nnz) { set_error("ssrs_potential_solve: gathered row lengths do not match the local rows"); return SSRS_ERR_CUDA; }
+    AMG_TRY(copy_d2d(col + starts[R], L.col, sizeof(int) * (size_t)L.nnz, st));
+    AMG_TRY(copy_d2d(val + starts[R], L.val, sizeof(double) * (size_t)L.nnz, st));
+    for (int q = 0; q <= P.n; ++q) offs[q] = starts[q] * (i64)sizeof(int);
+    if (comm->allgather(comm->ctx, col, offs, (void*)st) != 0) { set_error("ssrs_potential_solve: all-gather of the coarse columns failed"); return SSRS_ERR_CUDA; }
+    for (int q = 0; q <= P.n; ++q) offs[q] = starts[q] * (i64)sizeof(double);
+    if (comm->allgather(comm->ctx, val, offs, (void*)st) != 0) { set_error("ssrs_potential_solve: all-gather of the coarse values failed"); return SSRS_ERR_CUDA; }
+    L.rowptr = rp; L.col = col; L.val = val; L.nnz = nnz;
+    return build_ell(L, pool, st);            // over all rows; the owner-only arrays of the first build stay in the pool
 }
 
 // out = b - A x at free nodes (b = 0 there: the Dirichlet values live in x), 0 at Dirichlet nodes; *nrm2 = |out|^2
@@ -1173,6 +1297,9 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             H.lv[0].ref_hi[q] = q + 1 < P.n ? P.lo[q + 1] + cols : n;
         }
     }
+    // Distributed setup (default for the row-sharded solve): every rank builds its own rows of the distributed levels;
+    // SSRS_X_REDUNDANT_SETUP=1 keeps round 1's redundant setup (every rank builds everything) for A/B comparison.
+    const bool dist_setup = comm != nullptr && !(getenv("SSRS_X_REDUNDANT_SETUP") && atoi(getenv("SSRS_X_REDUNDANT_SETUP")) != 0);
     {
         float *wf, *dinv; double* wd; unsigned *wen, *wdd;
         Pool wtmp(st, true);                                   // float32 weights: only needed to form the diagonal
@@ -1183,7 +1310,16 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         AMG_ALLOC(wd, double, 4 * n);
         AMG_ALLOC(dinv, float, n);
         const FineGraph fgw = H.fine;
-        AMG_TRY(pfor2d(rows, cols, st, [=] SSRS_HD(int r, int c) {
+        // row-sharded: this rank reads the links of its own rows and of the halo row on each side, and — the cycle's
+        // fused first sweep forms x = omega dinv b on the halo rows locally — the diagonals of the halo rows, which
+        // need the links of one more row
+        int wr0 = 0, wr1 = rows, dr0 = 0, dr1 = rows;
+        if (dist_setup) {
+            const int R0s = (int)(H.lv[0].parts.lo[H.rank] / cols), R1s = (int)(H.lv[0].parts.lo[H.rank + 1] / cols);
+            wr0 = R0s > 2 ? R0s - 2 : 0; wr1 = R1s + 2 < rows ? R1s + 2 : rows;
+            dr0 = R0s > 1 ? R0s - 1 : 0; dr1 = R1s + 1 < rows ? R1s + 1 : rows;
+        }
+        AMG_TRY(pfor2d_rows(wr0, wr1, cols, st, [=] SSRS_HD(int r, int c) {
             const i64 i = (i64)r * cols + c;
             const float kc = fgw.kd[i];
             const bool hasE = c < cols - 1, hasN = r < rows - 1, hasW = c > 0;
@@ -1200,7 +1336,7 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         Fine32 F;
         F.w.en.p = wen; F.w.dd.p = wdd; F.dinv = dinv; F.kd = kd; F.rows = rows; F.cols = cols;
         const float *fE = wf, *fN = wf + n, *fNE = wf + 2 * n, *fNW = wf + 3 * n;
-        AMG_TRY(pfor2d(rows, cols, st, [=] SSRS_HD(int r, int c) {       // Jacobi diagonal of the float32 operator
+        AMG_TRY(pfor2d_rows(dr0, dr1, cols, st, [=] SSRS_HD(int r, int c) {       // Jacobi diagonal of the float32 operator
             const i64 i = (i64)r * cols + c;
             if (fgw.excluded(i)) { dinv[i] = 0.0f; return; }
             const bool hW = c > 0, hE = c < cols - 1, hS = r > 0, hN = r < rows - 1;
@@ -1240,12 +1376,17 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
                 if (q > 0 && L.ref_lo[q] < L.parts.lo[q - 1]) ok = false;
                 if (q + 1 < L.parts.n && L.ref_hi[q] > L.parts.lo[q + 2]) ok = false;
             }
-            if (!ok) { distributed = false; H.lrep = l; }
+            if (!ok) {
+                distributed = false; H.lrep = l;
+                if (dist_setup) { const int rcg = gather_level(H, L, pool, st); if (rcg) return rcg; }    // every rank continues with the whole level
+            }
         }
+        SetupDist D;                                   // this level's rows are built by their owners only
+        if (dist_setup && distributed) { D.comm = comm; D.rank = comm->rank; D.size = comm->size; D.st = st; }
         Parts next;
         int rc;
-        if (l == 0) { FineGraph g = H.fine; if (!distributed) g.parts = Parts(); rc = coarsen(g, L, pool, theta, 8, 3, &next, st); }
-        else { CsrGraph g = csr_of(L); if (!distributed) g.parts = Parts(); rc = coarsen(g, L, pool, theta, 8, 3, &next, st); }
+        if (l == 0) { FineGraph g = H.fine; if (!distributed) g.parts = Parts(); rc = coarsen(g, L, pool, theta, 8, 3, &next, st, D); }
+        else { CsrGraph g = csr_of(L); if (!distributed) g.parts = Parts(); rc = coarsen(g, L, pool, theta, 8, 3, &next, st, D); }
         if (rc) return rc;
         if (L.nc < 1 || (double)L.nc > 0.9 * (double)L.n) {        // stalled: stop here
             pool.release(L.agg); pool.release(L.memptr); pool.release(L.mem);
@@ -1253,14 +1394,28 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
             break;
         }
         Level C;
-        rc = (l == 0) ? galerkin(H.fine, L, C, pool, st) : galerkin(csr_of(L), L, C, pool, st);
+        if (D.on()) {
+            // Galerkin rows need the aggregate ids of the columns in the neighbours' slabs
+            AMG_RC(exchange_ghosts(H, l, L.agg, sizeof(int)));
+            const i64 clo = next.lo[D.rank], chi = next.lo[D.rank + 1];
+            rc = (l == 0) ? galerkin(H.fine, L, C, pool, st, clo, chi) : galerkin(csr_of(L), L, C, pool, st, clo, chi);
+        } else rc = (l == 0) ? galerkin(H.fine, L, C, pool, st) : galerkin(csr_of(L), L, C, pool, st);
         if (rc) return rc;
-        total_nnz += C.nnz;
+        { double nz = (double)C.nnz; AMG_RC(D.gather(&nz, 1)); total_nnz += (i64)nz; }
         C.parts = next;
-        rc = build_ell(C, pool, st);
+        rc = build_ell(C, pool, st, D);
         if (rc) return rc;
         ell_total += C.ell_entries;
         H.lv.push_back(C);
+        // the cycle forms the ghost entries of a level's first sweep locally (x = omega dinv b): the ghost rows' inverse
+        // diagonals come from their owners
+        if (D.on()) AMG_RC(exchange_ghosts(H, (int)H.lv.size() - 1, H.lv.back().dinv, sizeof(float)));
+    }
+    if (dist_setup && distributed && H.lv.size() > 1) {
+        // the coarsest level is always redundant: if the hierarchy ended while still distributed, gather it now
+        distributed = false; H.lrep = (int)H.lv.size() - 1;
+        const int rcg = gather_level(H, H.lv.back(), pool, st);
+        if (rcg) return rcg;
     }
     {
         Level& C = H.lv.back();
@@ -1308,7 +1463,8 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     double floor2 = 0.0, bmax = 0.0;
     for (int64_t q = 0; q < n_bnodes; ++q) bmax = fabs(bvalues_host[q]) > bmax ? fabs(bvalues_host[q]) : bmax;
     { const float* dinv = H.f32.dinv; const double scale = 0.5 * 2.220446049250313e-16 * bmax;
-      AMG_TRY(preduce_sum(n, st, &floor2, [=] SSRS_HD(i64 i) { const double di = (double)dinv[i]; const double e = di > 0.0 ? scale / di : 0.0; return e * e; })); }
+      AMG_TRY(preduce_sum_range(I0, I1, st, &floor2, [=] SSRS_HD(i64 i) { const double di = (double)dinv[i]; const double e = di > 0.0 ? scale / di : 0.0; return e * e; }));
+      AMG_RC(allsum(&floor2, nullptr)); }
     const double floor_rel = (r0 > 0.0) ? sqrt(floor2) / r0 : 0.0;
     if (trace) fprintf(stderr, "ssrs_potential_solve: r0 %.3e attainable relative residual ~ %.3e\n", r0, floor_rel);
     // The fraction is set by accuracy, measured against the refined truth of the 1000 x 1200 / 10 m system

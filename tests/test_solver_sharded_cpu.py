@@ -1,6 +1,7 @@
 """Row-sharded potential solve on CPU: ssrs_b200/csrc/potential.cu compiled with -DSSRS_HOST_EMU, one process per
 rank, `ssrs_comm` callbacks over gloo (tests/hostemu.py).  The sharded solve must reproduce the reference's
-golden potential and the single-rank solve to float32-rounding level, on every rank (each returns the full raster)."""
+golden potential and the single-rank solve to float32-rounding level, on every rank (each returns the full raster), and
+the distributed setup must build exactly the hierarchy of the redundant one (bit-identical potential, same iterations)."""
 import os
 import subprocess
 import sys
@@ -50,6 +51,14 @@ rc1, phi1, st1, _ = hostemu.solve(K, bn, bv)
 assert np.abs(phi.astype(np.float64) - phi1).max() <= 2.0 * ULP
 assert phi.min() >= 0.0 and phi.max() <= 1000.0
 assert calls["exchange"] > n0["exchange"] and calls["allreduce"] > n0["allreduce"] and calls["allgather"] > n0["allgather"]
+# the distributed setup (every rank builds its own rows of the distributed levels) against round 1's redundant setup
+# (every rank builds everything): the same hierarchy, hence bit-identical iterates
+os.environ["SSRS_X_REDUNDANT_SETUP"] = "1"
+rc2, phi2, st2, err2 = hostemu.solve_sharded(K, bn, bv, comm)
+del os.environ["SSRS_X_REDUNDANT_SETUP"]
+assert rc2 == 0, err2
+assert st2.iterations == st.iterations and st2.levels == st.levels and list(st2.level_rows[:st.levels]) == list(st.level_rows[:st.levels])
+assert np.array_equal(phi2, phi), float(np.abs(phi2.astype(np.float64) - phi).max())
 dist.barrier()
 if rank == 0:
     print("SHARDED_OK", calls, flush=True)
