@@ -777,6 +777,11 @@ struct Hierarchy {
     int lrep = 1 << 30;        // levels >= lrep are computed redundantly by every rank
     bool fuse_coarse_first = false;   // coarse levels: first sweep fused into the residual pass (two gathers per entry) or separate (one)
     stream_t st = nullptr;
+    // Levels >= lg (small, computed in full by this rank, no communication) run as ONE CUDA graph per cycle: their ~45
+    // launches of a few microseconds each are pure launch latency — 0.45 ms of a cycle, a fifth of an iteration of the
+    // 8-GPU solve, where the large levels' work is divided by eight and these are not.
+    int lg = 1 << 30;
+    void* gexec = nullptr;            // cudaGraphExec_t of the coarse part (device build)
 };
 
 inline CsrGraph csr_of(const Level& L) { CsrGraph g; g.rowptr = L.rowptr; g.col = L.col; g.val = L.val; g.n = L.n; g.parts = L.parts; return g; }
@@ -1013,7 +1018,9 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
         return SSRS_OK;
     };
     AMG_RC(restrict_to(0, H.resf));
-    for (int l = 1; l < nl - 1; ++l) {
+    // one level on the way down / up; `keep`: the smoothed iterate is copied back instead of swapping the level's two
+    // buffers, so that a captured graph stays valid from cycle to cycle
+    auto down = [&](int l) -> int {
         Level& L = H.lv[(size_t)l];
         const Ell e = ell_of(L);
         i64 i0, i1;
@@ -1036,10 +1043,9 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
             } else AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
             AMG_TRY(level_residual(L, i0, i1, L.b32, L.x32, L.r32, st));
         }
-        AMG_RC(restrict_to(l, L.r32));
-    }
-    AMG_RC(coarse_solve(H, H.lv[(size_t)nl - 1], st));
-    for (int l = nl - 2; l >= 1; --l) {
+        return restrict_to(l, L.r32);
+    };
+    auto up = [&](int l, bool keep) -> int {
         Level& L = H.lv[(size_t)l];
         i64 i0, i1;
         own_range(H, l, i0, i1);
@@ -1048,9 +1054,47 @@ int vcycle(Hierarchy& H, const double* rhs, double* out, stream_t st) {
         for (int s = 0; s < nul; ++s) {
             AMG_RC(exchange_ghosts(H, l, L.x32, sizeof(real)));
             AMG_TRY(level_jacobi(L, i0, i1, L.b32, L.x32, L.t32, om, st));
-            real* sw = L.x32; L.x32 = L.t32; L.t32 = sw;
+            if (keep) { real* xx = L.x32; const real* tt = L.t32; AMG_TRY(pfor_range(i0, i1, st, [=] SSRS_HD(i64 i) { xx[i] = tt[i]; })); }
+            else { real* sw = L.x32; L.x32 = L.t32; L.t32 = sw; }
+        }
+        return SSRS_OK;
+    };
+    const int lg = H.lg < nl ? (H.lg > 1 ? H.lg : 1) : nl;       // levels >= lg: the graph's part
+    for (int l = 1; l < nl - 1 && l < lg; ++l) AMG_RC(down(l));
+    auto coarse_part = [&](bool keep) -> int {
+        for (int l = lg; l < nl - 1; ++l) AMG_RC(down(l));
+        AMG_RC(coarse_solve(H, H.lv[(size_t)nl - 1], st));
+        for (int l = nl - 2; l >= lg; --l) AMG_RC(up(l, keep));
+        return SSRS_OK;
+    };
+    bool replayed = false;
+#ifndef SSRS_HOST_EMU
+    if (lg < nl) {
+        if (H.gexec == nullptr) {
+            // captured once per solve (same buffers, same branches every cycle), then replayed
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                H.lg = 1 << 30;              // this stream cannot be captured: plain launches from now on
+            } else {
+                const int rcc = coarse_part(true);
+                const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                if (rcc != 0 || ec != cudaSuccess || graph == nullptr) { cudaGetLastError(); set_error("ssrs_potential_solve: graph capture of the coarse levels failed"); return SSRS_ERR_CUDA; }
+                cudaGraphExec_t ge = nullptr;
+                const cudaError_t ei = cudaGraphInstantiate(&ge, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ei != cudaSuccess) { cudaGetLastError(); set_error("ssrs_potential_solve: graph instantiation failed"); return SSRS_ERR_CUDA; }
+                H.gexec = ge;
+            }
+        }
+        if (H.gexec != nullptr) {
+            AMG_TRY(cudaGraphLaunch((cudaGraphExec_t)H.gexec, st) == cudaSuccess ? 0 : -1);
+            replayed = true;
         }
     }
+#endif
+    if (!replayed) AMG_RC(coarse_part(false));
+    for (int l = (lg < nl - 1 ? lg : nl - 1) - 1; l >= 1; --l) AMG_RC(up(l, false));
     AMG_TRY(prolong_add32(H.lv[0], f0, f1, H.xf, H.lv[1].x32, H.overcorrect, st));
     for (int s = 0; s < nu - 1; ++s) {
         AMG_RC(exchange_ghosts(H, 0, H.xf, sizeof(real)));
@@ -1226,6 +1270,23 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
     if (!(rtol > 0.0)) rtol = 0.0;          // default: iterate to the attainable accuracy (see below)
     if (max_iter <= 0) max_iter = 300;
     stream_t st = (stream_t)stream;
+#ifndef SSRS_HOST_EMU
+    // The coarse levels of the cycle are replayed as a CUDA graph, which the legacy default stream cannot capture: a
+    // solve called on it runs on an internal stream ordered after it (the solve is synchronous, so ordering at the
+    // end is the final synchronisation).
+    if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+        static thread_local cudaStream_t own[64] = {nullptr};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("ssrs_potential_solve: bad device"); return SSRS_ERR_CUDA; }
+        if (own[dev] == nullptr && cudaStreamCreateWithFlags(&own[dev], cudaStreamNonBlocking) != cudaSuccess) { set_error("ssrs_potential_solve: cannot create a stream"); return SSRS_ERR_CUDA; }
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { set_error("ssrs_potential_solve: cannot create an event"); return SSRS_ERR_CUDA; }
+        cudaEventRecord(ev, st);
+        cudaStreamWaitEvent(own[dev], ev, 0);
+        cudaEventDestroy(ev);
+        st = own[dev];
+    }
+#endif
     const i64 n = (i64)rows * cols;
     const double t_begin = now_ms();
     const bool trace = getenv("SSRS_SOLVE_TRACE") != nullptr;      // per-iteration residuals on stderr
@@ -1430,6 +1491,15 @@ int solve_impl(const float* K, int rows, int cols, const int64_t* bnodes_host, c
         if (H.lrep < 1) H.lrep = 1;
         if (trace) fprintf(stderr, "ssrs_potential_solve: rank %d of %d, levels %d, redundant from level %d\n", H.rank, H.lv[0].parts.n, nl, H.lrep);
     }
+#ifndef SSRS_HOST_EMU
+    if (!(getenv("SSRS_X_NOGRAPH") && atoi(getenv("SSRS_X_NOGRAPH")) != 0)) {
+        // the graph's part of the cycle: from the first level that is small and computed in full by this rank
+        const int nl = (int)H.lv.size();
+        for (int l = 1; l < nl; ++l)
+            if ((comm == nullptr || l >= H.lrep) && H.lv[(size_t)l].n <= (i64)1 << 20) { H.lg = l; break; }
+    }
+    struct GraphGuard { Hierarchy& h; ~GraphGuard() { if (h.gexec) { cudaGraphExecDestroy((cudaGraphExec_t)h.gexec); h.gexec = nullptr; } } } graph_guard{H};
+#endif
     const double t_setup = now_ms();
 
     // ---- BiCGStab, right preconditioned ----
