@@ -125,11 +125,14 @@ SSRS_API int ssrs_potential_solve_f64(const float* conductivity, int rows, int c
 
 /* Row-sharded solve (BASELINE config 5): the grid's rows are split into `comm->size` contiguous
  * slabs; rank r owns slab r.  Every rank passes the SAME full conductivity raster (fields are replicated for the
- * stepping stage anyway) and receives the full potential.  The hierarchy is built redundantly on every rank
- * (identical, no communication; aggregates never straddle a slab boundary); the solve phase — V-cycles, operator
- * applications, Krylov vectors — runs on the owned slab only and exchanges one-row halos (fine level) or the few
+ * stepping stage anyway) and receives the full potential.  While a level is distributed (>= 1e6 rows) every rank
+ * builds and applies ITS rows of the hierarchy only — aggregates never straddle a slab boundary, so the setup needs
+ * the neighbours' aggregate ids along the slab boundary and a few per-part integers, nothing else —; the solve phase
+ * — V-cycles, operator applications, Krylov vectors — exchanges one-row halos (fine level) or the few
  * boundary-adjacent entries (coarse levels) with the two neighbouring ranks before each operator application,
- * plus one scalar all-reduce per inner product.  Levels below 1e6 rows are computed redundantly.
+ * plus one scalar all-reduce per inner product.  The first level below 1e6 rows is all-gathered and everything
+ * from there down is computed by every rank.  The result is bit-identical to a setup in which every rank builds
+ * everything (SSRS_X_REDUNDANT_SETUP=1 selects that, for comparison).
  *
  * ssrs_comm is the transport: plain function pointers, so the product uses NCCL over NVLink
  * (ssrs_comm_create_nccl) and the CPU test build drives the same solver code over gloo.
@@ -143,7 +146,7 @@ typedef struct ssrs_comm {
                     int64_t send_up_off, int64_t send_up_bytes, int64_t recv_up_off, int64_t recv_up_bytes,
                     int64_t send_dn_off, int64_t send_dn_bytes, int64_t recv_dn_off, int64_t recv_dn_bytes,
                     void* stream);
-    /* in-place sum of `count` HOST doubles over all ranks; blocking; bit-identical result on every rank */
+    /* in-place sum of `count` (<= 4 * SSRS_MAX_RANKS) HOST doubles over all ranks; blocking; bit-identical result on every rank */
     int (*allreduce_sum)(void* ctx, double* values_host, int32_t count, void* stream);
     /* in-place all-gather: rank r contributes bytes [offsets_host[r], offsets_host[r+1]) of `base` */
     int (*allgather)(void* ctx, void* base, const int64_t* offsets_host, void* stream);

@@ -53,7 +53,7 @@ NcclApi* api() {
 struct Ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, size = 1;
-    double* dscratch = nullptr;     // 8 doubles on the device for scalar reductions
+    double* dscratch = nullptr;     // kScalars doubles on the device for small reductions (inner products; per-part integers of the setup)
 };
 
 int nccl_fail(ncclResult_t r, const char* what) {
@@ -62,6 +62,8 @@ int nccl_fail(ncclResult_t r, const char* what) {
     return SSRS_ERR_CUDA;
 }
 #define SSRS_NCCL_TRY(expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) return nccl_fail(r_, #expr); } while (0)
+
+constexpr int kScalars = 4 * SSRS_MAX_RANKS;      // the distributed setup exchanges up to two integers per part
 
 int cb_exchange(void* vctx, void* base, int64_t su_off, int64_t su_n, int64_t ru_off, int64_t ru_n,
                 int64_t sd_off, int64_t sd_n, int64_t rd_off, int64_t rd_n, void* stream) {
@@ -83,7 +85,7 @@ int cb_allreduce_sum(void* vctx, double* host, int32_t count, void* stream) {
     Ctx* c = (Ctx*)vctx;
     NcclApi* a = api();
     cudaStream_t st = (cudaStream_t)stream;
-    if (count < 1 || count > 8) { set_error("ssrs_comm: all-reduce of %d scalars (1..8 supported)", count); return SSRS_ERR_INVALID; }
+    if (count < 1 || count > kScalars) { set_error("ssrs_comm: all-reduce of %d scalars (1..%d supported)", count, kScalars); return SSRS_ERR_INVALID; }
     SSRS_CUDA_TRY(cudaMemcpyAsync(c->dscratch, host, sizeof(double) * count, cudaMemcpyHostToDevice, st));
     SSRS_NCCL_TRY(a->AllReduce(c->dscratch, c->dscratch, (size_t)count, ncclDouble, ncclSum, c->comm, st));
     SSRS_CUDA_TRY(cudaMemcpyAsync(host, c->dscratch, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
@@ -139,7 +141,7 @@ extern "C" int ssrs_comm_create_nccl(const void* id128_host, int rank, int size,
     c->rank = rank; c->size = size;
     ncclResult_t r = a->CommInitRank(&c->comm, size, id, rank);
     if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
-    if (cudaMalloc(&c->dscratch, 8 * sizeof(double)) != cudaSuccess) { a->CommDestroy(c->comm); delete c; set_error("ssrs_comm_create_nccl: cudaMalloc failed"); return SSRS_ERR_CUDA; }
+    if (cudaMalloc(&c->dscratch, kScalars * sizeof(double)) != cudaSuccess) { a->CommDestroy(c->comm); delete c; set_error("ssrs_comm_create_nccl: cudaMalloc failed"); return SSRS_ERR_CUDA; }
     ssrs_comm* m = new ssrs_comm();
     m->rank = rank; m->size = size; m->ctx = c;
     m->exchange = cb_exchange; m->allreduce_sum = cb_allreduce_sum; m->allgather = cb_allgather; m->allreduce_u32 = cb_allreduce_u32;

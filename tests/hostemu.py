@@ -96,6 +96,8 @@ def gloo_comm():
 
     def allreduce(ctx, vals, count, stream):
         try:
+            if not 1 <= count <= 4 * 16:      # the bound include/ssrs_b200.h documents (4 * SSRS_MAX_RANKS)
+                raise ValueError(f"all-reduce of {count} scalars")
             t = torch.from_numpy(np.ctypeslib.as_array(vals, shape=(count,)))
             dist.all_reduce(t)
             calls["allreduce"] += 1

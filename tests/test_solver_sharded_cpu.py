@@ -66,7 +66,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world,rep_rows", [(2, 200), (3, 200), (2, 65536)])
+@pytest.mark.parametrize("world,rep_rows", [(2, 200), (3, 200), (8, 100), (2, 65536)])
 def test_sharded_solve_gloo(tmp_path, world, rep_rows):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
