@@ -110,14 +110,18 @@ __device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& l
             uc = clip_updraft(fc.x);
         }
     }
+#ifndef SSRS_X_NORED                   // (timing experiment: profiles/r02_step_experiments.txt)
     red_add1(P.presence + lin);
+#endif
 }
 
 // MEM1: track_dirn_restrict == 1 (the default): the mask is exactly the three candidates of the last move, so
 // no history register, no mask arithmetic.
 template <bool HAS_FIELDS, bool EXACT, bool MEM1>
+// 5 CTAs of 128 threads per SM (96 registers, nothing spilled): measured 2 % faster in the ring than 6 (80 registers,
+// 92 bytes spilled) and than 4 (profiles/r02_step_experiments.txt) — the kernel is not occupancy-bound
 #ifndef SSRS_STEP_MINB
-#define SSRS_STEP_MINB 6
+#define SSRS_STEP_MINB 5
 #endif
 __global__ void __launch_bounds__(128, SSRS_STEP_MINB) step_tracks_kernel(const TrackParams P) {
     const unsigned n_in = P.in_count != nullptr ? *P.in_count : (unsigned)P.n_tracks;
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(128, SSRS_STEP_MINB) step_tracks_kernel(const 
     __syncthreads();
     long long t = 0;
     const int nr = P.rows, nc = P.cols;
+
     const int kmax = P.kmax;
     const int kstop = min(kmax, P.kcap);                           // fast-lane budgets end at the phase cap
     unsigned long long steps_local = 0;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(128, SSRS_STEP_MINB) step_tracks_kernel(const 
     const bool fast_lane = HAS_FIELDS && !EXACT && MEM1 && P.nu_is_one && P.uniforms == nullptr && P.traj == nullptr &&
                            P.presence != nullptr;
     // While a lane has budget its state lives in the same registers in fast-lane form: `row` holds the linear cell index,
-    // `k` the pair counter k / 2, `last` the previous move's slot (the kernel sits at the register limit of 6 CTAs/SM).
+    // `k` the pair counter k / 2, `last` the previous move's slot (registers: 96 at 5 CTAs/SM).
     bool done = false, in_fast = false;
     int budget = 0;
     float2 fcen = make_float2(0.f, 0.f);
