@@ -291,6 +291,8 @@ def build_fields_gpu(a, torch, world=1, w=None, check_sharded=False):
         info[key] = (time.perf_counter() - t0) * 1e3
     info["potential_stats"] = stats
     info["potential_sharded_over"] = world
+    if sharded:
+        info["potential_halo_mode"] = D.halo_mode()       # 'peer': halos stored into the neighbours' memory; 'nccl': send/recv
     if sharded and check_sharded:
         # correctness of the row-sharded solve, outside any timed region: against this GPU's own single-GPU solve
         ref, _ = solve_potential_device(up, 0.0, sharded=False)

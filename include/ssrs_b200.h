@@ -166,6 +166,12 @@ SSRS_API int ssrs_potential_solve_sharded(const float* conductivity, int rows, i
 SSRS_API int ssrs_nccl_unique_id(void* id128_host);
 SSRS_API int ssrs_comm_create_nccl(const void* id128_host, int rank, int size, ssrs_comm** comm_out);
 SSRS_API int ssrs_comm_destroy(ssrs_comm* comm);
+/* How this communicator exchanges halos: 1 = over peer memory (each rank maps its neighbours' staging blocks through
+ * CUDA IPC; one kernel per exchange stores the boundary ranges into the neighbours' memory over NVLink, releases a
+ * sequence number there, waits for theirs and copies the arrived ranges into the ghost entries; chosen with
+ * SSRS_COMM_HALO=peer in the environment of ssrs_comm_create_nccl, when every rank can map its neighbours),
+ * 0 = grouped ncclSend/ncclRecv (the default), -1 = not a communicator of ssrs_comm_create_nccl. */
+SSRS_API int ssrs_comm_halo_mode(const ssrs_comm* comm);
 
 /* Presence-map reduction over the ranks that stepped disjoint blocks of tracks: in-place
  * sum of the uint32 count raster, one collective per (case, realisation) map.  Counts are integers, so the

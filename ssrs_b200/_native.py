@@ -39,6 +39,7 @@ EXPORTS = {
     "ssrs_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ssrs_comm_create_nccl": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ssrs_comm_destroy": (C.c_int, [C.c_void_p]),
+    "ssrs_comm_halo_mode": (C.c_int, [C.c_void_p]),
     "ssrs_presence_allreduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ssrs_step_tracks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                    C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64, C.c_void_p, C.c_int64,

@@ -97,6 +97,17 @@ def native_comm():
     return _native_comm
 
 
+def halo_mode() -> str:
+    """How the native communicator exchanges the sharded solve's halos: 'peer' (stores into the neighbours' memory over
+    NVLink, one kernel per exchange; SSRS_COMM_HALO=peer), 'nccl' (grouped ncclSend/ncclRecv, the default) or
+    'none' (single rank)."""
+    comm = native_comm()
+    if comm is None:
+        return "none"
+    from . import _native as N
+    return {1: "peer", 0: "nccl"}.get(int(N.load().ssrs_comm_halo_mode(comm)), "none")
+
+
 def destroy_native_comm() -> None:
     global _native_comm
     if _native_comm is not None:

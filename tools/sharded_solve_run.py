@@ -47,6 +47,7 @@ if world > 1:
     pres = torch.full((rows, cols), rank + 1, dtype=torch.int32, device="cuda")
     D.presence_allreduce(pres)
     out["presence_allreduce_ok"] = bool((pres == world * (world + 1) // 2).all().item())
+    out["halo_mode"] = D.halo_mode()
     dist.barrier()
 if rank == 0:
     print(json.dumps(out), flush=True)
