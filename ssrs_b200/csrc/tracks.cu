@@ -117,13 +117,18 @@ __device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& l
 
 // MEM1: track_dirn_restrict == 1 (the default): the mask is exactly the three candidates of the last move, so
 // no history register, no mask arithmetic.
-template <bool HAS_FIELDS, bool EXACT, bool MEM1>
 // 5 CTAs of 128 threads per SM (96 registers, nothing spilled): measured 2 % faster in the ring than 6 (80 registers,
-// 92 bytes spilled) and than 4 (profiles/r02_step_experiments.txt) — the kernel is not occupancy-bound
+// 92 bytes spilled) and than 4 (profiles/r02_step_experiments.txt) — the kernel is not occupancy-bound.  The 6-CTA
+// instantiation is kept for launches whose tracks fit 6 resident CTAs per SM but not 5 (100k tracks on 148 SMs): there
+// the 5-CTA grid would step the last 5 % of the tracks in a second, nearly empty round.
 #ifndef SSRS_STEP_MINB
 #define SSRS_STEP_MINB 5
 #endif
-__global__ void __launch_bounds__(128, SSRS_STEP_MINB) step_tracks_kernel(const TrackParams P) {
+#ifndef SSRS_STEP_HYBRID
+#define SSRS_STEP_HYBRID 1
+#endif
+template <bool HAS_FIELDS, bool EXACT, bool MEM1, int MINB = SSRS_STEP_MINB>
+__global__ void __launch_bounds__(128, MINB) step_tracks_kernel(const TrackParams P) {
     const unsigned n_in = P.in_count != nullptr ? *P.in_count : (unsigned)P.n_tracks;
     if ((unsigned)(blockIdx.x * blockDim.x) >= n_in) return;       // surplus CTA of a late phase: nothing to step
     // per previous move: element offsets of its three candidates, their packed indices, distance factors and
@@ -473,7 +478,15 @@ int step_tracks_impl(const float* fields, int rows, int cols, const int32_t* sta
     SSRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
     if (per_sm < 1) per_sm = 1;
     long long blocks = cdiv(n_tracks, threads);
-    const long long cap = (long long)sm_count() * per_sm;
+    long long cap = (long long)sm_count() * per_sm;
+    void (*kern0)(const TrackParams) = kern;              // first phase (or the only launch): every track is in it
+    long long blocks0 = blocks < cap ? blocks : cap;
+    if (SSRS_STEP_HYBRID && blocks > cap && fields != nullptr && !exact && mem1) {
+        int per_sm6 = 0;
+        void (*k6)(const TrackParams) = step_tracks_kernel<true, false, true, SSRS_STEP_MINB + 1>;
+        SSRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm6, k6, threads, 0));
+        if (blocks <= (long long)sm_count() * per_sm6) { kern0 = k6; blocks0 = blocks; }     // one round instead of two
+    }
     if (blocks > cap) blocks = cap;
     P.in_count = nullptr; P.in_list = nullptr; P.out_list = nullptr; P.out_count = nullptr; P.kcap = 2147483647;
     if (workspace == nullptr || !mem1) {
@@ -483,7 +496,7 @@ int step_tracks_impl(const float* fields, int rows, int cols, const int32_t* sta
         if (rc != SSRS_OK) return rc;
         P.in_head = reinterpret_cast<unsigned*>(slot);
         SSRS_CUDA_TRY(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st));
-        kern<<<(int)blocks, threads, 0, st>>>(P);
+        kern0<<<(int)blocks0, threads, 0, st>>>(P);
         SSRS_CUDA_TRY(cudaGetLastError());
         return SSRS_OK;
     }
@@ -500,7 +513,8 @@ int step_tracks_impl(const float* fields, int rows, int cols, const int32_t* sta
         P.in_count = p == 0 ? nullptr : counters + 2 * p + 1;
         P.out_count = counters + 2 * (p + 1) + 1;
         P.kcap = caps[p];
-        kern<<<(int)blocks, threads, 0, st>>>(P);
+        if (p == 0) kern0<<<(int)blocks0, threads, 0, st>>>(P);
+        else kern<<<(int)blocks, threads, 0, st>>>(P);
     }
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
