@@ -118,14 +118,18 @@ __device__ __forceinline__ void fast_step(const TrackParams& P, const FastLut& l
 // MEM1: track_dirn_restrict == 1 (the default): the mask is exactly the three candidates of the last move, so
 // no history register, no mask arithmetic.
 // 5 CTAs of 128 threads per SM (96 registers, nothing spilled): measured 2 % faster in the ring than 6 (80 registers,
-// 92 bytes spilled) and than 4 (profiles/r02_step_experiments.txt) — the kernel is not occupancy-bound.  The 6-CTA
-// instantiation is kept for launches whose tracks fit 6 resident CTAs per SM but not 5 (100k tracks on 148 SMs): there
-// the 5-CTA grid would step the last 5 % of the tracks in a second, nearly empty round.
+// 92 bytes spilled) and than 4 (profiles/r02_step_experiments.txt) — the kernel is not occupancy-bound.  The denser
+// instantiations (6, 7, 8 CTAs: 80, 72, 64 registers) are kept for the FIRST phase of launches whose tracks fit that many
+// resident CTAs per SM but not 5 (100k tracks on 148 SMs need 6, 125k need 7): all tracks of a first phase take the same
+// number of steps, so a 5-CTA grid would step the excess in a second, mostly empty round.
 #ifndef SSRS_STEP_MINB
 #define SSRS_STEP_MINB 5
 #endif
 #ifndef SSRS_STEP_HYBRID
 #define SSRS_STEP_HYBRID 1
+#endif
+#ifndef SSRS_STEP_HYBRID_MAX
+#define SSRS_STEP_HYBRID_MAX 3          // denser instantiations tried for the first phase: 6, 7, 8 CTAs per SM
 #endif
 template <bool HAS_FIELDS, bool EXACT, bool MEM1, int MINB = SSRS_STEP_MINB>
 __global__ void __launch_bounds__(128, MINB) step_tracks_kernel(const TrackParams P) {
@@ -482,10 +486,15 @@ int step_tracks_impl(const float* fields, int rows, int cols, const int32_t* sta
     void (*kern0)(const TrackParams) = kern;              // first phase (or the only launch): every track is in it
     long long blocks0 = blocks < cap ? blocks : cap;
     if (SSRS_STEP_HYBRID && blocks > cap && fields != nullptr && !exact && mem1) {
-        int per_sm6 = 0;
-        void (*k6)(const TrackParams) = step_tracks_kernel<true, false, true, SSRS_STEP_MINB + 1>;
-        SSRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm6, k6, threads, 0));
-        if (blocks <= (long long)sm_count() * per_sm6) { kern0 = k6; blocks0 = blocks; }     // one round instead of two
+        // the smallest denser instantiation that holds every track at once, if there is one: one round instead of two
+        void (*dense[3])(const TrackParams) = {step_tracks_kernel<true, false, true, SSRS_STEP_MINB + 1>,
+                                               step_tracks_kernel<true, false, true, SSRS_STEP_MINB + 2>,
+                                               step_tracks_kernel<true, false, true, SSRS_STEP_MINB + 3>};
+        for (int j = 0; j < SSRS_STEP_HYBRID_MAX; ++j) {
+            int occ = 0;
+            SSRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense[j], threads, 0));
+            if (blocks <= (long long)sm_count() * occ) { kern0 = dense[j]; blocks0 = blocks; break; }
+        }
     }
     if (blocks > cap) blocks = cap;
     P.in_count = nullptr; P.in_list = nullptr; P.out_list = nullptr; P.out_count = nullptr; P.kcap = 2147483647;
