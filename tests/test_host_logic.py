@@ -25,6 +25,17 @@ def test_library_exports_every_declared_symbol():
     _native.load()
 
 
+def test_host_only_entry_points_answer_without_a_gpu():
+    """Entry points that are pure host arithmetic: halo transport query of a missing communicator, phase count of the
+    phased stepper, workspace and table sizes."""
+    from ssrs_b200 import _native
+    lib = _native.load()
+    assert lib.ssrs_comm_halo_mode(None) == -1
+    assert lib.ssrs_step_phase_count(5000, 6000, 0) == 34 and lib.ssrs_step_phase_count(3, 3, 0) == 0
+    assert lib.ssrs_walk_workspace_bytes(1000) == 2 * 1000 * 16 + 4096
+    assert lib.ssrs_walk_table_bytes(5000, 6000) == 5000 * 6000 * 64
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "ssrs_b200")
     for dirpath, _, files in os.walk(pkg):
