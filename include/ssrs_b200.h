@@ -314,6 +314,23 @@ SSRS_API int ssrs_interp_wind_nearest(const double* px, const double* py, const 
                                       int npoints, double x0, double y0, double resolution, int rows, int cols,
                                       float* wspeed, float* wdirn, void* stream);
 
+/* The same for Config.wtk_interp_type = 'cubic' (scipy griddata(method='cubic') = CloughTocher2DInterpolator with
+ * tol 1e-6, maxiter 400, no rescaling: gradients at the sites by Gauss-Seidel sweeps that minimise the curvature along
+ * the triangulation's edges, then a C1 piecewise cubic on every triangle; NaN outside the convex hull).  Besides the
+ * arguments of ssrs_interp_wind: neighbors int32 [ntriangles][3] (scipy.spatial.Delaunay.neighbors: the triangle
+ * opposite vertex k, -1 on the hull) and the sites' adjacency in CSR form (Delaunay.vertex_neighbor_vertices:
+ * vertex_nb_indptr int32 [npoints+1], vertex_nb_indices int32 [indptr[npoints]]), all on the device.  ct_scratch:
+ * ssrs_interp_wind_cubic_scratch_bytes(npoints, ntriangles) bytes on the device, 32-byte aligned; on return (stream
+ * order) it holds the gradients float64 [2][npoints][2] (east, north), the Bezier ordinates float64
+ * [ntriangles][2][20] and, last, two int32 sweep counts (0 = the 400 sweeps did not reach the tolerance: scipy warns
+ * and uses the last iterate, and so does this entry point). */
+SSRS_API int64_t ssrs_interp_wind_cubic_scratch_bytes(int npoints, int ntriangles);
+SSRS_API int ssrs_interp_wind_cubic(const double* px, const double* py, const double* east, const double* north, int npoints,
+                                    const int32_t* triangles, const int32_t* neighbors, int ntriangles,
+                                    const int32_t* vertex_nb_indptr, const int32_t* vertex_nb_indices, double x0, double y0,
+                                    double resolution, int rows, int cols, int32_t* owner_scratch, void* ct_scratch,
+                                    float* wspeed, float* wdirn, void* stream);
+
 /* compute_thermals (ssrs/layers.py:188-214) in two steps: the random seeds (Philox4x32-10 keyed by (seed, cell):
  * same distribution as the reference's np.random draws, not the same stream) and the deterministic
  * scipy.ndimage.gaussian_filter(sigma, mode='constant', truncate) smoothing.  tmp: float32 [rows][cols];

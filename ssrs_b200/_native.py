@@ -31,6 +31,10 @@ EXPORTS = {
                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_interp_wind_nearest": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssrs_interp_wind_cubic_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "ssrs_interp_wind_cubic": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssrs_thermal_seeds": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ssrs_gaussian_blur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                      C.c_void_p, C.c_void_p]),

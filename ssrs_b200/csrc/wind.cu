@@ -9,6 +9,10 @@
 //      1.2e8 cells per wind case — runs here: triangles are rasterised over their bounding boxes (a cell on a
 //      shared edge goes to the lower triangle index, both sides interpolate the same value there), then every
 //      cell evaluates its triangle in float64.  HBM-bound: 4 B index + 8 B output per cell.
+//      wtk_interp_type = 'cubic' (griddata's Clough-Tocher scheme, clough_tocher.cuh) shares the rasterisation:
+//      gradients at the sites by the same Gauss-Seidel sweeps as scipy (one warp per wind component; the sweep is
+//      sequential over the sites by definition), 19 Bezier ordinates per triangle and component, then one cubic
+//      per cell and component.
 //
 // f-3  ssrs_thermal_seeds + ssrs_gaussian_blur — compute_thermals (ssrs/layers.py:188-214): per cell inside the
 //      10 % border a thermal is seeded with probability 1/(int(wtfactor) - 1), wtfactor = 1000 + |aspect-180|/180
@@ -17,6 +21,7 @@
 //      global stream cell by cell, so only the distribution can be reproduced: draws here are
 //      Philox4x32-10 keyed by (seed, cell).  The blur is deterministic and matches scipy's to float32 rounding.
 #include "common.cuh"
+#include "clough_tocher.cuh"
 
 #include <math.h>
 
@@ -93,6 +98,84 @@ __global__ void __launch_bounds__(256) interp_wind_kernel(const double* __restri
         barycentric(T, x0 + c * res, y0 + r * res, c0, c1, c2);
         const double e = c0 * east[T.i0] + c1 * east[T.i1] + c2 * east[T.i2];
         const double n = c0 * north[T.i0] + c1 * north[T.i1] + c2 * north[T.i2];
+        const double two_pi = 6.283185307179586;
+        s = (float)sqrt(e * e + n * n);                                         // simulator.py:787-788
+        d = (float)(fmod(atan2(e, n) + two_pi, two_pi) * (180.0 / 3.141592653589793));   // :789-791
+    }
+    wspeed[i] = s;
+    wdirn[i] = d;
+}
+
+// ---- Clough-Tocher ('cubic') ---------------------------------------------------------------------------
+struct WarpLanes {                                 // the lanes of one warp share a vertex's neighbour loop
+    __device__ int lane() const { return threadIdx.x; }
+    __device__ int lanes() const { return 32; }
+    __device__ double sum(double v) const {        // butterfly: every lane ends with the same bits (a + b == b + a)
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ void sync() const { __syncwarp(); }
+};
+
+// CTA 0: easterly component, CTA 1: northerly.  grad: [2][npoints][2]; sweeps: [2] (0 = maxiter reached)
+__global__ void __launch_bounds__(32) ct_gradients_kernel(const double* px, const double* py, const double* east,
+                                                          const double* north, int npoints, const int* nb_indptr,
+                                                          const int* nb_indices, int maxiter, double tol, double* grad,
+                                                          int* sweeps) {
+    WarpLanes w;
+    const int comp = blockIdx.x;
+    const int n = ct::estimate_gradients(w, px, py, comp == 0 ? east : north, npoints, nb_indptr, nb_indices, maxiter, tol,
+                                         grad + (size_t)comp * 2 * npoints);
+    if (threadIdx.x == 0) sweeps[comp] = n;
+}
+
+// one thread per (triangle, component): the triangle's 19 Bezier ordinates
+__global__ void __launch_bounds__(128) ct_coefficients_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                                              const double* __restrict__ east, const double* __restrict__ north,
+                                                              int npoints, const int* __restrict__ tri,
+                                                              const int* __restrict__ neighbors, int ntri,
+                                                              const double* __restrict__ grad, double* __restrict__ coef) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * ntri) return;
+    const int t = k >> 1, comp = k & 1;
+    const Tri T = load_tri(px, py, tri, t);
+    const int v[3] = {T.i0, T.i1, T.i2};
+    const double* val = comp == 0 ? east : north;
+    const double* g = grad + (size_t)comp * 2 * npoints;
+    double p[3][2], f[3], df[3][2], c[3][3];
+    int has_nb[3];
+    for (int j = 0; j < 3; ++j) {
+        p[j][0] = px[v[j]]; p[j][1] = py[v[j]];
+        f[j] = val[v[j]];
+        df[j][0] = g[2 * v[j]]; df[j][1] = g[2 * v[j] + 1];
+        const int nb = neighbors[3 * t + j];                 // the triangle across the side opposite vertex j
+        has_nb[j] = nb >= 0;
+        c[j][0] = c[j][1] = c[j][2] = 0.0;
+        if (nb >= 0) {
+            const int a = tri[3 * nb], b = tri[3 * nb + 1], d = tri[3 * nb + 2];
+            barycentric(T, (px[a] + px[b] + px[d]) / 3, (py[a] + py[b] + py[d]) / 3, c[j][0], c[j][1], c[j][2]);
+        }
+    }
+    ct::coefficients(p, f, df, has_nb, c, coef + (size_t)k * ct::COEF_STRIDE);
+}
+
+__global__ void __launch_bounds__(256) interp_wind_cubic_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                                                const int* __restrict__ tri, double x0, double y0, double res,
+                                                                int rows, int cols, const int* __restrict__ owner,
+                                                                const double* __restrict__ coef, float* __restrict__ wspeed,
+                                                                float* __restrict__ wdirn) {
+    const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+    if (r >= rows || c >= cols) return;
+    const long long i = (long long)r * cols + c;
+    const int t = owner[i];
+    float s = nanf(""), d = nanf("");                 // outside the convex hull: griddata's fill value
+    if (t != NO_TRIANGLE) {
+        const Tri T = load_tri(px, py, tri, t);
+        double b0, b1, b2;
+        barycentric(T, x0 + c * res, y0 + r * res, b0, b1, b2);
+        const double* ce = coef + (size_t)t * 2 * ct::COEF_STRIDE;       // neighbouring cells share the triangle: L1 hits
+        const double e = ct::evaluate(ce, b0, b1, b2);
+        const double n = ct::evaluate(ce + ct::COEF_STRIDE, b0, b1, b2);
         const double two_pi = 6.283185307179586;
         s = (float)sqrt(e * e + n * n);                                         // simulator.py:787-788
         d = (float)(fmod(atan2(e, n) + two_pi, two_pi) * (180.0 / 3.141592653589793));   // :789-791
@@ -249,6 +332,41 @@ extern "C" int ssrs_interp_wind(const double* px, const double* py, const double
     dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 8));
     interp_wind_kernel<<<grid, dim3(32, 8), 0, st>>>(px, py, east, north, triangles, x0, y0, resolution, rows, cols,
                                                      owner_scratch, wspeed, wdirn);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    return SSRS_OK;
+}
+
+extern "C" int64_t ssrs_interp_wind_cubic_scratch_bytes(int npoints, int ntriangles) {
+    if (npoints < 0 || ntriangles < 0) return 0;
+    // gradients [2][npoints][2], ordinates [ntriangles][2][20], sweep counts [2] (int32)
+    return (int64_t)sizeof(double) * (4 * (int64_t)npoints + 2 * (int64_t)ct::COEF_STRIDE * ntriangles + 1);
+}
+
+extern "C" int ssrs_interp_wind_cubic(const double* px, const double* py, const double* east, const double* north, int npoints,
+                                      const int32_t* triangles, const int32_t* neighbors, int ntriangles,
+                                      const int32_t* vertex_nb_indptr, const int32_t* vertex_nb_indices, double x0, double y0,
+                                      double resolution, int rows, int cols, int32_t* owner_scratch, void* ct_scratch,
+                                      float* wspeed, float* wdirn, void* stream) {
+    SSRS_REQUIRE(px && py && east && north && triangles && neighbors && vertex_nb_indptr && vertex_nb_indices &&
+                 owner_scratch && ct_scratch && wspeed && wdirn, "ssrs_interp_wind_cubic: NULL buffer");
+    SSRS_REQUIRE(npoints >= 3 && ntriangles >= 1 && rows > 0 && cols > 0 && resolution > 0.0, "ssrs_interp_wind_cubic: bad sizes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* grad = static_cast<double*>(ct_scratch);
+    double* coef = grad + 4 * (size_t)npoints;
+    int* sweeps = reinterpret_cast<int*>(coef + 2 * (size_t)ct::COEF_STRIDE * ntriangles);
+    ct_gradients_kernel<<<2, 32, 0, st>>>(px, py, east, north, npoints, vertex_nb_indptr, vertex_nb_indices, 400, 1e-6, grad,
+                                          sweeps);                                  // griddata's maxiter and tol
+    SSRS_CUDA_TRY(cudaGetLastError());
+    ct_coefficients_kernel<<<(unsigned)cdiv(2 * ntriangles, 128), 128, 0, st>>>(px, py, east, north, npoints, triangles, neighbors,
+                                                                      ntriangles, grad, coef);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    SSRS_CUDA_TRY(cudaMemsetAsync(owner_scratch, 0x7f, sizeof(int32_t) * (size_t)rows * cols, st));
+    const int blocks = ntriangles < sm_count() * 8 ? ntriangles : sm_count() * 8;
+    rasterise_triangles_kernel<<<blocks, 256, 0, st>>>(px, py, triangles, ntriangles, x0, y0, resolution, rows, cols, owner_scratch);
+    SSRS_CUDA_TRY(cudaGetLastError());
+    dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 8));
+    interp_wind_cubic_kernel<<<grid, dim3(32, 8), 0, st>>>(px, py, triangles, x0, y0, resolution, rows, cols, owner_scratch, coef,
+                                                           wspeed, wdirn);
     SSRS_CUDA_TRY(cudaGetLastError());
     return SSRS_OK;
 }

@@ -144,15 +144,27 @@ def delaunay_triangles(xlocs, ylocs):
     return np.ascontiguousarray(Delaunay(pts).simplices, dtype=np.int32)
 
 
+def delaunay_topology(xlocs, ylocs):
+    """The triangulation with the adjacency 'cubic' needs: (triangles [nt, 3], neighbors [nt, 3] — the triangle opposite
+    vertex k, -1 on the hull —, vertex_nb_indptr [n + 1], vertex_nb_indices), all int32.  Pass the tuple as `triangles=`
+    to reuse it for many wind cases."""
+    from scipy.spatial import Delaunay
+    pts = np.stack([np.asarray(xlocs, dtype=np.float64), np.asarray(ylocs, dtype=np.float64)], 1)
+    d = Delaunay(pts)
+    indptr, indices = d.vertex_neighbor_vertices
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return i32(d.simplices), i32(d.neighbors), i32(indptr), i32(indices)
+
+
 def interpolate_wind_to_grid(xlocs, ylocs, wspeed, wdirn, x0: float, y0: float, res: float, gridsize,
                              triangles=None, method: str = 'linear'):
     """Reference `Simulator._get_interpolated_wind_conditions` (`simulator.py:778-792`): wind speed/direction at
     scattered sites -> CUDA float32 rasters `[rows, cols]` (speed, direction in degrees).  `method` is
     `Config.wtk_interp_type`: 'linear' (the default; NaN outside the sites' convex hull; `triangles` may be passed to
-    reuse one triangulation for many wind cases) or 'nearest' (closest site, defined everywhere).  scipy's 'cubic'
-    (Clough-Tocher) is not built."""
-    if method not in ('linear', 'nearest'):
-        raise NotImplementedError(f"wtk_interp_type={method!r}: 'linear' (the Config default) and 'nearest' run on the GPU")
+    reuse one triangulation for many wind cases), 'nearest' (closest site, defined everywhere) or 'cubic' (griddata's
+    Clough-Tocher scheme: C1 piecewise cubic, NaN outside the hull; `triangles` is then `delaunay_topology`'s tuple)."""
+    if method not in ('linear', 'nearest', 'cubic'):
+        raise ValueError(f"Unknown interpolation method {method!r} for 2 dimensional data")      # griddata's error
     torch = N.require_cuda()
     lib = N.load()
     x = np.ascontiguousarray(xlocs, dtype=np.float64)
@@ -173,13 +185,33 @@ def interpolate_wind_to_grid(xlocs, ylocs, wspeed, wdirn, x0: float, y0: float, 
                                              float(res), rows, cols, N.ptr(out_s), N.ptr(out_d), N.current_stream()),
                 "ssrs_interp_wind_nearest")
         return out_s, out_d
-    tri = delaunay_triangles(x, y) if triangles is None else np.ascontiguousarray(triangles, dtype=np.int32)
     rows, cols = int(gridsize[0]), int(gridsize[1])
     dev = lambda a: torch.from_numpy(a).to("cuda")
-    dx, dy, de, dn, dt = dev(x), dev(y), dev(east), dev(north), dev(tri)
     owner = torch.empty((rows, cols), dtype=torch.int32, device="cuda")
     out_s = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
     out_d = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+    if method == 'cubic':
+        topo = delaunay_topology(x, y) if triangles is None else triangles
+        if not (isinstance(topo, tuple) and len(topo) == 4):
+            raise ValueError("method='cubic' takes the (triangles, neighbors, indptr, indices) tuple of delaunay_topology")
+        tri, nbr, indptr, indices = (np.ascontiguousarray(a, dtype=np.int32) for a in topo)
+        if tri.ndim != 2 or tri.shape[1] != 3 or nbr.shape != tri.shape or indptr.shape != (x.size + 1,):
+            raise ValueError("inconsistent triangulation arrays")
+        dx, dy, de, dn = dev(x), dev(y), dev(east), dev(north)
+        dt, dnb, dip, dix = dev(tri), dev(nbr), dev(indptr), dev(indices)
+        nbytes = int(lib.ssrs_interp_wind_cubic_scratch_bytes(x.size, tri.shape[0]))
+        scratch = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+        N.check(lib.ssrs_interp_wind_cubic(N.ptr(dx), N.ptr(dy), N.ptr(de), N.ptr(dn), x.size, N.ptr(dt), N.ptr(dnb),
+                                           tri.shape[0], N.ptr(dip), N.ptr(dix), float(x0), float(y0), float(res), rows, cols,
+                                           N.ptr(owner), N.ptr(scratch), N.ptr(out_s), N.ptr(out_d), N.current_stream()),
+                "ssrs_interp_wind_cubic")
+        sweeps = scratch[-1:].view(torch.int32).cpu().numpy()
+        if (sweeps == 0).any():
+            import warnings
+            warnings.warn("Gradient estimation did not converge, the results may be inaccurate")      # scipy's wording
+        return out_s, out_d
+    tri = delaunay_triangles(x, y) if triangles is None else np.ascontiguousarray(triangles, dtype=np.int32)
+    dx, dy, de, dn, dt = dev(x), dev(y), dev(east), dev(north), dev(tri)
     N.check(lib.ssrs_interp_wind(N.ptr(dx), N.ptr(dy), N.ptr(de), N.ptr(dn), x.size, N.ptr(dt), tri.shape[0], float(x0),
                                  float(y0), float(res), rows, cols, N.ptr(owner), N.ptr(out_s), N.ptr(out_d),
                                  N.current_stream()), "ssrs_interp_wind")

@@ -186,14 +186,13 @@ class Simulator(Config):
             self._wind_cases = wind_cases
             self._wind_points = None
             if wind_points is not None:
-                if self.wtk_interp_type not in ('linear', 'nearest'):
-                    # documented rejection: griddata's 'cubic' (Clough-Tocher) is not built; failing in
-                    # the constructor beats failing after the terrain work
-                    raise ValueError(f"wtk_interp_type={self.wtk_interp_type!r} is not supported by ssrs_b200: "
-                                     f"use 'linear' (the reference's default, config.py:44) or 'nearest'")
-                from .layers import delaunay_triangles
+                if self.wtk_interp_type not in ('linear', 'nearest', 'cubic'):
+                    # griddata's own methods (config.py:60); failing in the constructor beats failing after the terrain work
+                    raise ValueError(f"Unknown interpolation method {self.wtk_interp_type!r} for 2 dimensional data")
+                from .layers import delaunay_topology, delaunay_triangles
                 xl, yl = (np.asarray(v, dtype=np.float64) for v in wind_points)
-                self._wind_points = (xl, yl, delaunay_triangles(xl, yl))       # one triangulation for all cases
+                topo = delaunay_topology if self.wtk_interp_type == 'cubic' else delaunay_triangles
+                self._wind_points = (xl, yl, topo(xl, yl))                     # one triangulation for all cases
             self.compute_orographic_updrafts_using_wtk()
         else:
             print(f'Uniform mode: Wind speed = {self.uniform_windspeed} m/s')

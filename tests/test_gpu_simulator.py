@@ -147,6 +147,19 @@ def test_snapshot_mode_wind_sites_and_thermals(tmp_path):
     sim2 = Simulator(cfg.__class__(**{**cfg.__dict__, "run_name": "snap3"}), elevation=z, wind_points=(xl, yl),
                      wind_cases={"y2014m12d01h15": (spd, drn)})
     assert np.array_equal(np.load(os.path.join(sim2.mode_data_dir, "y2014m12d01h15_r0_thermals.npy")), th)
+    # Config.wtk_interp_type = 'cubic' (config.py:60): the orograph follows griddata(method='cubic'); an unknown method
+    # fails in the constructor with griddata's error
+    over = lambda **kw: cfg.__class__(**{**cfg.__dict__, "thermals_realization_count": 0, **kw})
+    sim3 = Simulator(over(run_name="snap4", wtk_interp_type="cubic"), elevation=z, wind_points=(xl, yl),
+                     wind_cases={"y2014m12d01h15": (spd, drn)})
+    ws_c, wd_c = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg, method='cubic')
+    _, _, oro_c, _ = O.updraft_pipeline(z, res, ws_c, wd_c, 0.75)
+    got_c = np.load(os.path.join(sim3.mode_data_dir, "y2014m12d01h15_orograph.npy"))
+    assert np.abs(got_c - oro_c).max() <= 1e-5 * oro_c.max()
+    assert np.abs(oro_c - oro_ref).max() > 1e-4 * oro_ref.max()          # and differs from the linear one
+    with pytest.raises(ValueError):
+        Simulator(over(run_name="snap5", wtk_interp_type="quintic"), elevation=z, wind_points=(xl, yl),
+                  wind_cases={"y2014m12d01h15": (spd, drn)})
 
 
 def test_seasonal_mode_three_cases(tmp_path):

@@ -136,8 +136,73 @@ def test_gpu_wind_interpolation_nearest(golden):
         dd = np.abs(wd - ref_d); dd = np.minimum(dd, 360.0 - dd)
         bad |= dd > 1e-5 * 360.0
         assert bad.sum() <= 2, bad.sum()
-    with pytest.raises(NotImplementedError):
-        layers.interpolate_wind_to_grid(g["a_x"], g["a_y"], g["a_speed"], g["a_dirn"], 0.0, 0.0, res, (rows, cols), method='cubic')
+    with pytest.raises(ValueError):          # griddata's own error for a method it does not know
+        layers.interpolate_wind_to_grid(g["a_x"], g["a_y"], g["a_speed"], g["a_dirn"], 0.0, 0.0, res, (rows, cols), method='quintic')
+
+
+def _ct_case(seed, n, narrow=False):
+    rng = np.random.RandomState(seed)
+    pts = rng.rand(n, 2) * np.array([6000.0, 5000.0])
+    if narrow:                              # a sliver on the hull and two nearly coincident sites
+        pts[0] = (3000.0, -1e-3); pts[1] = (10.0, 0.0); pts[2] = (5990.0, 0.0); pts[3] = pts[4] + 1e-6
+    vals = 8.0 + 3.0 * np.sin(pts[:, 0] / 900.0) * np.cos(pts[:, 1] / 700.0) + 0.3 * rng.randn(n)
+    return pts, vals
+
+
+@pytest.mark.parametrize("seed,n,narrow", [(0, 12, False), (1, 60, False), (2, 400, False), (3, 60, True)])
+def test_clough_tocher_arithmetic_matches_scipy(seed, n, narrow):
+    """Config.wtk_interp_type = 'cubic' (config.py:60 -> griddata(method='cubic'), simulator.py:772): the lines of
+    csrc/clough_tocher.cuh, compiled for the host, against scipy's CloughTocher2DInterpolator — the gradient sweeps
+    (same count, same values) and the cubic inside every triangle, on the hull's triangles and in slivers."""
+    from scipy.interpolate import CloughTocher2DInterpolator
+    from scipy.spatial import Delaunay
+    import ctemu
+    pts, vals = _ct_case(seed, n, narrow)
+    tri = Delaunay(pts)
+    ref = CloughTocher2DInterpolator(tri, vals)          # griddata's defaults: tol 1e-6, maxiter 400, no rescaling
+    grad, sweeps = ctemu.gradients(pts, vals, *tri.vertex_neighbor_vertices)
+    assert sweeps > 0
+    scale = np.abs(ref.grad).max()
+    assert np.abs(grad - ref.grad[:, 0, :]).max() <= 1e-12 * scale
+    rng = np.random.RandomState(seed + 100)
+    q = rng.rand(4000, 2) * np.array([6400.0, 5400.0]) - 200.0            # some queries fall outside the hull
+    simplex = tri.find_simplex(q)
+    got = ctemu.interpolate(pts, vals, grad, tri.simplices, tri.neighbors, q[:, 0], q[:, 1], simplex)
+    want = ref(q)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and (simplex < 0).any() and (simplex >= 0).sum() > 1000
+    ok = ~np.isnan(want)
+    assert np.abs(got[ok] - want[ok]).max() <= 1e-9 * np.abs(want[ok]).max()
+    # the interpolant reproduces the site values (two sites 1e-6 m apart: the barycentric coordinates lose digits)
+    used = np.unique(tri.simplices)
+    s_at = tri.find_simplex(pts[used])
+    at_sites = ctemu.interpolate(pts, vals, grad, tri.simplices, tri.neighbors, pts[used, 0], pts[used, 1], s_at)
+    assert np.abs(at_sites - vals[used]).max() <= (1e-6 if narrow else 1e-9) * np.abs(vals).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_gpu_wind_interpolation_cubic(golden, case):
+    """'cubic' through the C-ABI (gradient sweeps, Bezier ordinates and the per-cell cubic all on the device) against
+    griddata(method='cubic') on every cell of the fixtures' grids; case b leaves the hull."""
+    from ssrs_b200 import layers
+    g = golden("wind_thermals")
+    rows, cols, res, xg, yg = _grid(g)
+    xl, yl, spd, drn = (g[f"{case}_{k}"] for k in ("x", "y", "speed", "dirn"))
+    ws, wd = layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), method='cubic')
+    ws, wd = ws.cpu().numpy().astype(np.float64), wd.cpu().numpy().astype(np.float64)
+    ref_s, ref_d = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg, method='cubic')
+    nan_ref = np.isnan(ref_s)
+    assert (np.isnan(ws) != nan_ref).sum() <= 2                   # cells within rounding of a hull edge
+    assert nan_ref.any() == (case == "b")
+    ok = ~nan_ref & ~np.isnan(ws)
+    assert np.abs(ws[ok] - ref_s[ok]).max() <= 1e-5 * np.abs(ref_s[ok]).max()
+    dd = np.abs(wd[ok] - ref_d[ok])
+    dd = np.minimum(dd, 360.0 - dd)
+    weight = ref_s[ok] / np.abs(ref_s[ok]).max()                  # the direction of a vanishing vector is ill-conditioned
+    assert (dd * np.minimum(1.0, weight * 1e3)).max() <= 1e-5 * 360.0
+    # it is not the linear interpolant in disguise
+    lin_s, _ = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg)
+    assert np.nanmax(np.abs(lin_s - ref_s)) > 1e-3 * np.nanmax(ref_s)
 
 
 @pytest.mark.gpu
@@ -176,3 +241,17 @@ def test_gpu_wind_interpolation_full_size():
     got_d = wd[::40, ::40].cpu().numpy().astype(np.float64)
     dd = np.abs(got_d - ref_d); dd = np.minimum(dd, 360.0 - dd)
     assert ((np.abs(got_s - ref_s) > 1e-6 * ref_s.max()) | (dd > 1e-5 * 360.0)).sum() <= 2
+    # 'cubic' at the same size (one triangulation + adjacency for all cases)
+    topo = layers.delaunay_topology(xl, yl)
+    layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), triangles=topo, method='cubic')
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ws, wd = layers.interpolate_wind_to_grid(xl, yl, spd, drn, 0.0, 0.0, res, (rows, cols), triangles=topo, method='cubic')
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"interpolate_wind_to_grid(cubic) {len(xl)} sites -> {rows}x{cols}: {dt * 1e3:.2f} ms")
+    assert not torch.isnan(ws).any() and not torch.isnan(wd).any()
+    ref_s, ref_d = O.interpolated_wind_conditions(xl, yl, spd, drn, xg, yg, method='cubic')
+    got_s = ws[::40, ::40].cpu().numpy().astype(np.float64)
+    got_d = wd[::40, ::40].cpu().numpy().astype(np.float64)
+    assert np.abs(got_s - ref_s).max() <= 1e-5 * ref_s.max()
+    dd = np.abs(got_d - ref_d); dd = np.minimum(dd, 360.0 - dd)
+    assert dd.max() <= 1e-5 * 360.0
