@@ -16,7 +16,6 @@
 
 #ifndef SSRS_HOST_EMU
 #include <cuda_runtime.h>
-#include <cub/device/device_scan.cuh>
 #endif
 
 namespace ssrs {
@@ -298,23 +297,98 @@ inline int preduce2d_sum2_rows(int r0, int r1, int cols, stream_t s, double* out
     *out0 = h[0]; *out1 = h[1];
     return 0;
 }
+// In-place exclusive prefix sum of int64 (AMG setup: row pointers, aggregate numbering).  Three launches over tiles
+// of 2048 items: per-tile sums (coalesced, strided items), ONE CTA that turns the tile sums into tile offsets and the
+// grand total, then every tile scans itself (a thread owns 8 consecutive items) on top of its offset.  Integer sums:
+// the result does not depend on the order.
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// exclusive scan of one value per thread over the CTA (blockDim.x a multiple of 32, <= 1024); *total on every thread
+__device__ __forceinline__ int64_t block_exclusive_scan_i64(int64_t v, int64_t* total) {
+    __shared__ int64_t warp_excl[32];
+    __shared__ int64_t cta_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int64_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    __syncthreads();                                   // readers of a previous call are done with the shared words
+    if (lane == 31) warp_excl[warp] = incl;            // this warp's sum
+    __syncthreads();
+    if (warp == 0) {
+        const int64_t w = lane < nwarps ? warp_excl[lane] : 0;
+        int64_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t up = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += up;
+        }
+        warp_excl[lane] = wi - w;                      // sum of the warps before this one
+        if (lane == 31) cta_total = wi;
+    }
+    __syncthreads();
+    *total = cta_total;
+    return warp_excl[warp] + incl - v;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const int64_t* __restrict__ data, int64_t n,
+                                                                      int64_t* __restrict__ tile_sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) v += data[i];
+    }
+    int64_t total;
+    block_exclusive_scan_i64(v, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// one CTA: tile_sums[0..ntiles) -> exclusive offsets in place, tile_sums[ntiles] = grand total
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(int64_t* tile_sums, int64_t ntiles) {
+    int64_t carry = 0;
+    for (int64_t c0 = 0; c0 < ntiles; c0 += blockDim.x) {
+        const int64_t i = c0 + threadIdx.x;
+        const int64_t v = i < ntiles ? tile_sums[i] : 0;
+        int64_t total;
+        const int64_t excl = block_exclusive_scan_i64(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + excl;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int64_t* data, int64_t n, const int64_t* __restrict__ tile_offsets) {
+    const int64_t first = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t item[SCAN_ITEMS];
+    int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        item[k] = first + k < n ? data[first + k] : 0;
+        mine += item[k];
+    }
+    int64_t total;
+    int64_t run = tile_offsets[blockIdx.x] + block_exclusive_scan_i64(mine, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (first + k < n) data[first + k] = run;
+        run += item[k];
+    }
+}
 inline int exclusive_scan_i64(int64_t* data, int64_t n, int64_t* total, stream_t s) {
     if (n <= 0) { *total = 0; return 0; }
-    int64_t last_in = 0, last_out = 0;
-    if (cudaMemcpyAsync(&last_in, data + n - 1, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
-    size_t tmp_bytes = 0;
-    if (cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, data, data, n, s) != cudaSuccess) return -1;
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles > 2147483647LL) return -1;
     Arena& ar = arena(true);
     const Arena::Mark mk = ar.mark();
-    void* tmp = ar.alloc(tmp_bytes ? tmp_bytes : 1);
-    if (!tmp) return -1;
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, data, data, n, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_out, data + n - 1, 8, cudaMemcpyDeviceToHost, s);
+    int64_t* tiles = (int64_t*)ar.alloc(sizeof(int64_t) * (size_t)(ntiles + 1));
+    if (!tiles) return -1;
+    scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(data, n, tiles);
+    scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(tiles, ntiles);
+    scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(data, n, tiles);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(total, tiles + ntiles, 8, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     ar.release_to(mk);
-    if (e != cudaSuccess) return -1;
-    *total = last_in + last_out;
-    return 0;
+    return e == cudaSuccess ? 0 : -1;
 }
 __host__ __device__ __forceinline__ int atomic_add_int(int* p, int v) {
 #ifdef __CUDA_ARCH__
