@@ -190,3 +190,38 @@ def test_seasonal_mode_three_cases(tmp_path):
     summ = sim.plot_presence_map(radius=500.)
     ref = np.sum(maps, axis=0)
     assert np.allclose(summ, ref / ref.max(), rtol=1e-5, atol=1e-6)
+
+
+def test_potential_cache_is_keyed_by_content(tmp_path, capsys):
+    """The reference reuses `<id>_potential.npy` by id string alone (simulator.py:264-272) and would step tracks on a
+    potential computed for other terrain.  Here the cache entry carries a content key: same inputs -> reused,
+    other terrain under the same run name -> recomputed, a raster without a key -> stale, force_potential -> recomputed."""
+    from ssrs_b200 import Config, Simulator
+    from ssrs_b200.synth import synthetic_dem
+    rows, cols, res = 120, 160, 100.0
+    cfg = Config(run_name="cache", out_dir=str(tmp_path), sim_seed=3, region_width_km=(16., 12.), resolution=res,
+                 sim_mode="uniform", uniform_windspeed=10., uniform_winddirn=270., track_direction=0., track_count=32,
+                 track_start_region=(2, 14, 0.5, 1))
+    z1, z2 = synthetic_dem(rows, cols, res, seed=1), synthetic_dem(rows, cols, res, seed=2)
+
+    def run(z, **kw):
+        capsys.readouterr()
+        sim = Simulator(cfg, elevation=z, **kw)
+        sim.simulate_tracks()
+        out = capsys.readouterr().out
+        fname = sim._get_potential_fname("s10d270", 0, sim.mode_data_dir)
+        return ("Found saved potential" in out, "Computing potential" in out, np.load(f"{fname}.npy"), fname,
+                sim.presence_counts())
+
+    found, computed, pot1, fname, pres1 = run(z1)
+    assert computed and not found and os.path.exists(f"{fname}.key")
+    found, computed, pot1b, _, pres1b = run(z1)
+    assert found and not computed and np.array_equal(pot1b, pot1) and np.array_equal(pres1b, pres1)
+    found, computed, pot2, _, _ = run(z2)                       # other terrain, same id string
+    assert computed and not found and not np.array_equal(pot2, pot1)
+    key2 = open(f"{fname}.key").read()
+    found, computed, pot2b, _, _ = run(z2, force_potential=True)
+    assert computed and not found and np.abs(pot2b - pot2).max() <= 1e-5 * 1000.0 and open(f"{fname}.key").read() == key2
+    os.remove(f"{fname}.key")                                   # a raster the reference (or an older run) left behind
+    found, computed, _, _, _ = run(z2)
+    assert computed and not found and os.path.exists(f"{fname}.key")
