@@ -531,7 +531,7 @@ def main():
         achieved = STEP_BYTES * (steps_rank / a.steps) / (per_launch_ms * 1e-3) / 1e9
         nl = phase_launches(rows, cols, a.mode)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "f64 probabilities on f32 fields", "data": "synthetic",
             "config": {"workload": workload_text(w, world), "grid": [rows, cols], "tracks_per_step": n_total,
@@ -542,6 +542,8 @@ def main():
                                     "single": "ssrs_step_tracks (one launch per batch)",
                                     "walk": "ssrs_transition_table + ssrs_walk_tracks (table rebuilt every step)"}[a.mode],
                        "steps_in_flight": ring.slots,
+                       "warmup_executed": f"{warm + 1} untimed steps: max(--warmup, one per ring slot), then one batch alone "
+                                          f"for launch_ms_alone",
                        "parallelism": f"tracks block-partitioned over {world} GPU(s), fields replicated, presence all-reduce "
                                       f"per step on a side stream"},
             "fields": finfo,
