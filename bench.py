@@ -111,6 +111,16 @@ def resolve_workload(a, world):
     return w
 
 
+def workload_config(w, world):
+    """`config` of the JSON line: the workload and nothing run-specific, so that it is identical in both arms (the driver
+    compares the two arms' `config`); what a run did beyond that is under the line's `run` key."""
+    mb = w["rows"] * w["cols"] * 4 / 1e6
+    l2 = (f"inputs_exceed_l2 (fields {2 * mb:.0f} MB + presence {mb:.0f} MB > 126 MB; every timed step is another realisation "
+          f"and writes another presence raster)") if 3 * mb > 126 else \
+         f"inputs fit L2 ({3 * mb:.1f} MB): a custom small grid, not a BASELINE workload"
+    return {"workload": workload_text(w, world), "grid": [w["rows"], w["cols"]], "tracks_per_step": w["n_total"], "l2": l2}
+
+
 def workload_text(w, world):
     wind = {"uniform": "uniform mode, wind 10 m/s from 270 deg", "snapshot": "snapshot mode, wind at a jittered 2 km lattice of "
             "sites interpolated to the grid", "seasonal": "seasonal mode, one sampled wind condition per step"}[w["wind"]]
@@ -534,18 +544,17 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "f64 probabilities on f32 fields", "data": "synthetic",
-            "config": {"workload": workload_text(w, world), "grid": [rows, cols], "tracks_per_step": n_total,
-                       "tracks_per_gpu": n_rank, "track_steps_per_step": steps_all / a.steps,
-                       "l2": "inputs_exceed_l2 (fields 240 MB + presence 120 MB > 126 MB)",
-                       "rng": "philox4x32-10 keyed by (seed, global track id, step); timed step i uses seed + 1 + i (another realisation per step)",
-                       "stepping": {"phased": "ssrs_step_tracks_phased (survivors compacted between phases)",
-                                    "single": "ssrs_step_tracks (one launch per batch)",
-                                    "walk": "ssrs_transition_table + ssrs_walk_tracks (table rebuilt every step)"}[a.mode],
-                       "steps_in_flight": ring.slots,
-                       "warmup_executed": f"{warm + 1} untimed steps: max(--warmup, one per ring slot), then one batch alone "
-                                          f"for launch_ms_alone",
-                       "parallelism": f"tracks block-partitioned over {world} GPU(s), fields replicated, presence all-reduce "
-                                      f"per step on a side stream"},
+            "config": workload_config(w, world),
+            "run": {"tracks_per_gpu": n_rank, "track_steps_per_step": steps_all / a.steps,
+                    "rng": "philox4x32-10 keyed by (seed, global track id, step); timed step i uses seed + 1 + i (another realisation per step)",
+                    "stepping": {"phased": "ssrs_step_tracks_phased (survivors compacted between phases)",
+                                 "single": "ssrs_step_tracks (one launch per batch)",
+                                 "walk": "ssrs_transition_table + ssrs_walk_tracks (table rebuilt every step)"}[a.mode],
+                    "steps_in_flight": ring.slots,
+                    "warmup_executed": f"{warm + 1} untimed steps: max(--warmup, one per ring slot), then one batch alone "
+                                       f"for launch_ms_alone",
+                    "parallelism": f"tracks block-partitioned over {world} GPU(s), fields replicated, presence all-reduce "
+                                   f"per step on a side stream"},
             "fields": finfo,
             "roofline": {"bound": "hbm", "kernel": "step_tracks_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
@@ -743,8 +752,8 @@ def reference_arm(a, w, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f64 probabilities on f32 fields", "data": "synthetic",
-            "config": {"workload": workload_text(w, world), "grid": [w["rows"], w["cols"]], "potential": pot_src,
-                       "stencil_numpy_s": stencil_s},
+            "config": workload_config(w, world),
+            "run": {"potential": pot_src, "stencil_numpy_s": stencil_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": f"{n_sample} of the step's tracks per step ({steps_done // max(1, a.steps)} track-steps), {how}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
