@@ -25,6 +25,41 @@ def test_library_exports_every_declared_symbol():
     _native.load()
 
 
+def test_bindings_match_the_header_prototypes():
+    """Every ctypes prototype in ssrs_b200/_native.py against the C prototype in include/ssrs_b200.h: same number of
+    parameters, same kind per position (pointer / int / int64 / uint64 / float / double) and the same return type — an
+    argument dropped or widened in a binding otherwise shows up as a garbage stream handle at run time."""
+    from ssrs_b200 import _native
+    header = open(os.path.join(ROOT, "include", "ssrs_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict((m.group(2), (m.group(1).strip(), m.group(3)))
+                  for m in re.finditer(r"SSRS_API\s+([\w\s\*]+?)\b(ssrs_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(_native.EXPORTS)
+
+    def kind_of_c(decl):
+        decl = " ".join(decl.split())
+        if "*" in decl:
+            return "ptr"
+        base = decl.rsplit(" ", 1)[0] if " " in decl else decl          # drop the parameter name
+        base = base.replace("const ", "").replace("unsigned long long", "uint64_t").strip()
+        return {"int": "int", "int32_t": "int", "int64_t": "i64", "long long": "i64", "uint64_t": "u64", "float": "f32",
+                "double": "f64"}[base]
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_int32: "int", ctypes.c_int64: "i64", ctypes.c_uint64: "u64",
+                ctypes.c_float: "f32", ctypes.c_double: "f64"}[t]
+
+    for name, (ret, params) in sorted(protos.items()):
+        restype, argtypes = _native.EXPORTS[name]
+        c_params = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        assert len(c_params) == len(argtypes), (name, len(c_params), len(argtypes))
+        for i, (c, t) in enumerate(zip(c_params, argtypes)):
+            assert kind_of_c(c) == kind_of_ctypes(t), (name, i, c.strip(), t)
+        assert kind_of_c(ret + " x") == kind_of_ctypes(restype), (name, ret, restype)
+
+
 def test_host_only_entry_points_answer_without_a_gpu():
     """Entry points that are pure host arithmetic: halo transport query of a missing communicator, phase count of the
     phased stepper, workspace and table sizes."""
