@@ -60,6 +60,32 @@ def test_bindings_match_the_header_prototypes():
         assert kind_of_c(ret + " x") == kind_of_ctypes(restype), (name, ret, restype)
 
 
+def test_integration_sketch_calls_match_the_header():
+    """The ctypes sketch in INTEGRATION.md (what a maintainer of the reference would paste): it parses, and every
+    `lib.ssrs_*(...)` call passes as many arguments as the header's prototype has parameters."""
+    import ast
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    assert blocks
+    header = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "ssrs_b200.h")).read(), flags=re.S)
+    nparams = {m.group(1): (0 if m.group(2).strip() in ("", "void") else m.group(2).count(",") + 1)
+               for m in re.finditer(r"SSRS_API\s+[\w\s\*]+?\b(ssrs_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)}
+    seen = set()
+    for block in blocks:
+        tree = ast.parse(block)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("ssrs_") \
+                    and isinstance(node.func.value, ast.Name) and node.func.value.id == "lib":
+                n = 0
+                for arg in node.args:
+                    # `*map(_p, out)` spreads the four output rasters of ssrs_updraft
+                    n += 4 if isinstance(arg, ast.Starred) else 1
+                assert node.func.attr in nparams, node.func.attr
+                assert n == nparams[node.func.attr], (node.func.attr, n, nparams[node.func.attr])
+                seen.add(node.func.attr)
+    assert {"ssrs_updraft", "ssrs_potential_solve", "ssrs_step_tracks", "ssrs_interleave_fields"} <= seen
+
+
 def test_host_only_entry_points_answer_without_a_gpu():
     """Entry points that are pure host arithmetic: halo transport query of a missing communicator, phase count of the
     phased stepper, workspace and table sizes."""
