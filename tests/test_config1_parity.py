@@ -100,6 +100,21 @@ def test_c_oracle_distribution(c1):
     _check_distribution(c1, runs)
 
 
+@pytest.mark.parametrize("dirn,mem,nu", [(0.0, 1, 1.0), (45.0, 1, 1.0), (0.0, 3, 1.0), (0.0, 1, 0.5)])
+def test_production_arithmetic_picks_the_reference_moves(c1, dirn, mem, nu):
+    """The link between the two parity statements: on the reference's own config-1 fields and IDENTICAL uniform streams
+    (Philox, same seed) the production arithmetic (normalisations cancelled; what the GPU steps with, bit for bit) and the
+    reference's exact operation order (pinned step for step by the reference's trajectories above) choose the same move
+    at every step of every track — ~8e5 steps per run — so a production run IS the reference's algorithm
+    (movmodel.py:264-318) on another random stream, not merely a process with a similar distribution."""
+    for seed in (101, 202):
+        exact = OC.step_tracks(c1["U32"], c1["P32"], SHAPE, _starts(c1), dirn, mem, nu, seed=seed, nthreads=8, fast=False)
+        prod = OC.step_tracks(c1["U32"], c1["P32"], SHAPE, _starts(c1), dirn, mem, nu, seed=seed, nthreads=8, fast=True)
+        assert exact["total_steps"] == prod["total_steps"] > 5e5
+        assert np.array_equal(exact["traj_len"], prod["traj_len"])
+        assert np.array_equal(exact["presence"], prod["presence"])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_gpu_step_for_step(c1):
