@@ -115,6 +115,24 @@ def test_production_arithmetic_picks_the_reference_moves(c1, dirn, mem, nu):
         assert np.array_equal(exact["presence"], prod["presence"])
 
 
+def test_production_arithmetic_picks_the_reference_moves_at_10m(golden):
+    """The same at the resolution of the large configs (1000 x 1200 cells at 10 m, the refined-truth fixture's fields):
+    two thirds of the float32 potential are plateaus there, so the fallback chain of movmodel.py:228-240 decides far
+    more steps than at 100 m — and still every one of ~1.2e7 steps agrees."""
+    g = golden("potential_truth10m")
+    U, P = g["K32"], g["phi_truth32"]
+    rng = np.random.RandomState(5)
+    n = 2000
+    starts = np.stack([rng.randint(2, 40, n), rng.randint(2, U.shape[1] - 2, n)], 1).astype(np.int32)
+    for seed in (7, 8):
+        for mem, nu in ((1, 1.0), (2, 1.0), (1, 0.3)):
+            exact = OC.step_tracks(U, P, U.shape, starts, 0.0, mem, nu, seed=seed, nthreads=8, fast=False)
+            prod = OC.step_tracks(U, P, U.shape, starts, 0.0, mem, nu, seed=seed, nthreads=8, fast=True)
+            assert exact["total_steps"] == prod["total_steps"] > 1.5e6
+            assert np.array_equal(exact["traj_len"], prod["traj_len"])
+            assert np.array_equal(exact["presence"], prod["presence"])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_gpu_step_for_step(c1):
