@@ -154,6 +154,24 @@ class Simulator(Config):
         self.terrain_layers = {'Elevation': 'injected'}
         self.turbines = None
         self.region = None
+        # reference :107-127 — attribute surface only: the WTK download is outside the hot path and wind
+        # arrives through wind_cases=; case ids that are time stamps give back the reference's `dtimes`
+        self.wtk_layers = {
+            'wspeed': f'windspeed_{str(int(self.wtk_orographic_height))}m',
+            'wdirn': f'winddirection_{str(int(self.wtk_orographic_height))}m',
+            'pressure': f'pressure_{str(int(self.wtk_thermal_height))}m',
+            'temperature': f'temperature_{str(int(self.wtk_thermal_height))}m',
+            'blheight': 'boundary_layer_height',
+            'surfheatflux': 'surface_heat_flux',
+        }
+        self.wtk = None
+        self.dtimes = None
+        if wind_cases:
+            from datetime import datetime
+            try:
+                self.dtimes = [datetime.strptime(str(k), self.time_format) for k in wind_cases]
+            except ValueError:
+                self.dtimes = None
         if elevation is None:
             raise ValueError("ssrs_b200.Simulator needs elevation= (terrain download is outside the hot path; "
                              "inject the DEM raster [rows=north, cols=east])")

@@ -86,6 +86,43 @@ def test_integration_sketch_calls_match_the_header():
     assert {"ssrs_updraft", "ssrs_potential_solve", "ssrs_step_tracks", "ssrs_interleave_fields"} <= seen
 
 
+def test_simulator_constructor_host_part(tmp_path, monkeypatch):
+    """The part of `Simulator.__init__` that runs before the first CUDA call (reference simulator.py:40-127): output
+    directories, the JSON dump of the configuration, grid size and bounds, and the attribute surface plot code relies on
+    (SURVEY App. E).  The constructor is stopped at its CUDA gate — there is no CPU path behind it."""
+    import json
+    from datetime import datetime
+    import ssrs_b200.simulator as S
+    from ssrs_b200 import Config, Simulator
+
+    class Gate(Exception):
+        pass
+
+    def gate():
+        raise Gate()
+    monkeypatch.setattr(S.N, "require_cuda", gate)
+    z = np.zeros((120, 160), np.float32)
+    for mode, cases, dtimes in (("uniform", None, None),
+                                ("snapshot", {"y2014m12d01h15": (8.0, 270.0)}, [datetime(2014, 12, 1, 15)]),
+                                ("seasonal", {"case00": (8.0, 270.0), "case01": (6.0, 200.0)}, None)):
+        cfg = Config(run_name=f"host_{mode}", out_dir=str(tmp_path), sim_mode=mode, region_width_km=(16., 12.), resolution=100.)
+        sim = Simulator.__new__(Simulator)
+        with pytest.raises(Gate):
+            sim.__init__(cfg, elevation=z, wind_cases=cases)
+        assert sim.gridsize == (120, 160) and sim.bounds == (0.0, 0.0, 15900.0, 11900.0)
+        assert sim.extent == (0.0, 15900.0, 0.0, 11900.0)
+        assert os.path.isdir(sim.mode_data_dir) and sim.mode_data_dir.endswith(os.path.join("data", mode))
+        assert os.path.isdir(sim.mode_fig_dir)
+        with open(os.path.join(str(tmp_path), cfg.run_name, f"{cfg.run_name}.json")) as f:
+            dumped = json.load(f)
+        assert dumped["sim_mode"] == mode and dumped["resolution"] == 100.0 and "wtk_layers" not in dumped
+        assert sim.wtk_layers["wspeed"] == "windspeed_100m" and sim.wtk_layers["temperature"] == "temperature_100m"
+        assert sim.wtk is None and sim.dtimes == dtimes
+        assert Simulator.lonlat_crs == "EPSG:4326" and Simulator.time_format == "y%Ym%md%dh%H"
+    with pytest.raises(ValueError):            # terrain is injected, never downloaded
+        Simulator(Config(run_name="noelev", out_dir=str(tmp_path)))
+
+
 def test_host_only_entry_points_answer_without_a_gpu():
     """Entry points that are pure host arithmetic: halo transport query of a missing communicator, phase count of the
     phased stepper, workspace and table sizes."""
