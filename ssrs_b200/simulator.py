@@ -295,6 +295,12 @@ class Simulator(Config):
         return interpolate_wind_to_grid(xl, yl, wspeed, wdirn, self.bounds[0], self.bounds[1], self.resolution,
                                         self.gridsize, triangles=tri, method=self.wtk_interp_type)
 
+    def get_wtk_locs(self):
+        """Reference :711-716 — projected coordinates of the wind sites (here: the injected wind_points=)."""
+        if getattr(self, '_wind_points', None) is None:
+            raise ValueError("no wind sites: pass wind_points=(xlocs, ylocs) to the constructor")
+        return self._wind_points[0], self._wind_points[1]
+
     def compute_thermal_updrafts(self, case_id: str):
         """Reference :217-228.  Realisation r is keyed by (sim_seed, case, r): reproducible for sim_seed >= 0."""
         if self.thermals_realization_count > 0:

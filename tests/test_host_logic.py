@@ -121,6 +121,10 @@ def test_simulator_constructor_host_part(tmp_path, monkeypatch):
         assert Simulator.lonlat_crs == "EPSG:4326" and Simulator.time_format == "y%Ym%md%dh%H"
     with pytest.raises(ValueError):            # terrain is injected, never downloaded
         Simulator(Config(run_name="noelev", out_dir=str(tmp_path)))
+    with pytest.raises(ValueError):
+        sim.get_wtk_locs()
+    sim._wind_points = (np.arange(3.0), np.arange(3.0) + 1, None)
+    assert np.array_equal(sim.get_wtk_locs()[1], [1.0, 2.0, 3.0])
 
 
 def test_host_only_entry_points_answer_without_a_gpu():
